@@ -1,0 +1,153 @@
+"""Pins the oracle (numpy + C restatements) bit-for-bit against outputs of the reference's own
+Numba kernels, recorded in tests/golden/ by oracle/gen_golden.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle
+
+
+def _queries(z):
+    ptr = z["q_ptr"]
+    return [(z["q_terms"][ptr[i]:ptr[i + 1]], z["q_weights"][ptr[i]:ptr[i + 1]]) for i in range(len(ptr) - 1)]
+
+
+@pytest.fixture(scope="module")
+def bm25(golden_dir):
+    return np.load(os.path.join(golden_dir, "bm25_arrays.npz"))
+
+
+def test_bm25_numpy_bit_exact(bm25):
+    z = bm25
+    n_vocab = len(z["idf"])
+    csc = np_oracle.csr_to_csc(z["data"], z["indices"], z["indptr"], n_vocab)
+    for q, (t, w) in enumerate(_queries(z)):
+        qtf = np_oracle.dense_query(t, w, n_vocab)
+        s = np_oracle.bm25_scores(qtf, z["data"], z["indices"], z["indptr"], z["doc_lengths"], z["idf"],
+                                  float(z["k1"]), float(z["b"]), float(z["avgdl"]), csc=csc)
+        assert np.array_equal(s.view(np.uint32), z["ref_scores"][q].view(np.uint32)), f"query {q}"
+
+
+def test_bm25_c_bit_exact(bm25):
+    z = bm25
+    n_vocab = len(z["idf"])
+    for q, (t, w) in enumerate(_queries(z)):
+        qtf = np_oracle.dense_query(t, w, n_vocab)
+        s = c_oracle.bm25_scores(qtf, z["data"], z["indices"], z["indptr"], z["doc_lengths"], z["idf"],
+                                 float(z["k1"]), float(z["b"]), float(z["avgdl"]))
+        assert np.array_equal(s.view(np.uint32), z["ref_scores"][q].view(np.uint32)), f"query {q}"
+
+
+def test_bm25_fractional_inputs_bit_exact(golden_dir):
+    """fractional tf / doc lengths / idf / query weights, k1=0.9, b=0.4: pins the f64 evaluation order."""
+    z = np.load(os.path.join(golden_dir, "bm25_frac.npz"))
+    n_vocab = len(z["idf"])
+    for q, (t, w) in enumerate(_queries(z)):
+        qtf = np_oracle.dense_query(t, w, n_vocab)
+        for fn in (np_oracle.bm25_scores, c_oracle.bm25_scores):
+            s = fn(qtf, z["data"], z["indices"], z["indptr"], z["doc_lengths"], z["idf"], float(z["k1"]),
+                   float(z["b"]), float(z["avgdl"]))
+            assert np.array_equal(s.view(np.uint32), z["ref_scores"][q].view(np.uint32))
+
+
+def test_bm25_k1_1000_b0(bm25):
+    """registry 'tfidf' parameterisation (retriever_registry.py:593-595) through the same kernel."""
+    z = bm25
+    n_vocab = len(z["idf"])
+    for q, (t, w) in enumerate(_queries(z)[:4]):
+        qtf = np_oracle.dense_query(t, w, n_vocab)
+        for fn in (np_oracle.bm25_scores, c_oracle.bm25_scores):
+            s = fn(qtf, z["data"], z["indices"], z["indptr"], z["doc_lengths"], z["idf"], 1000.0, 0.0,
+                   float(z["avgdl"]))
+            assert np.array_equal(s.view(np.uint32), z["ref_scores_k1000"][q].view(np.uint32))
+
+
+def test_bm25_fixture_has_the_hard_cases(bm25):
+    z = bm25
+    assert (z["idf"] < 0).sum() >= 2                       # negative idf (df > N/2)
+    assert (np.diff(z["indptr"]) == 0).sum() >= 10         # empty docs keep a row
+    assert (z["ref_scores"] < 0).any() and (z["ref_scores"] == 0).any()
+
+
+def test_topk_values_match_reference(bm25):
+    """ids are only comparable where the reference's arbitrary tie order cannot matter: compare the
+    sorted score VALUES everywhere and the ids wherever the k+1 best scores are distinct."""
+    z = bm25
+    for q in range(z["ref_scores"].shape[0]):
+        s = z["ref_scores"][q]
+        for fn in (np_oracle.topk_canonical, c_oracle.topk):
+            idx, val = fn(s, 10)
+            assert np.array_equal(val, z["ref_top_val"][q])
+            assert np.array_equal(val, s[idx])
+            top11 = np.sort(s)[::-1][:11]
+            if len(np.unique(top11)) == 11:
+                assert np.array_equal(idx, z["ref_top_idx"][q])
+
+
+def test_topk_reference_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
+    for name in ("normal", "uniform", "zipfian", "bimodal", "k_ge_n", "big"):
+        s, k = z[f"{name}_scores"], int(z[f"{name}_k"])
+        for fn in (np_oracle.topk_canonical, c_oracle.topk):
+            idx, val = fn(s, k)
+            assert len(idx) == min(k, len(s))
+            assert np.array_equal(val, z[f"{name}_ref_val"]), name
+            if len(np.unique(s)) == len(s):                 # no ties at all -> ids are pinned too
+                assert np.array_equal(idx, z[f"{name}_ref_idx"]), name
+
+
+def test_topk_tie_rule():
+    s = np.array([1.0, 2.0, 2.0, -0.0, 0.0, np.nan, 2.0, 1.0], np.float32)
+    for fn in (np_oracle.topk_canonical, c_oracle.topk):
+        idx, val = fn(s, 8)
+        assert idx.tolist() == [1, 2, 6, 0, 7, 3, 4, 5]
+        idx, _ = fn(s, 2)
+        assert idx.tolist() == [1, 2]
+
+
+def test_tfidf_bit_exact(golden_dir):
+    z = np.load(os.path.join(golden_dir, "tfidf_arrays.npz"))
+    n_vocab = len(z["idf"])
+    ones = np.ones(n_vocab, np.float32)
+    for q, (t, w) in enumerate(_queries(z)):
+        qtf = np_oracle.dense_query(t, w, n_vocab)
+        for fn in (np_oracle.tfidf_scores, c_oracle.tfidf_scores):
+            s = fn(qtf, z["data"], z["indices"], z["indptr"], z["idf"])
+            assert np.array_equal(s.view(np.uint32), z["ref_scores"][q].view(np.uint32))
+            s = fn(qtf, z["data"], z["indices"], z["indptr"], ones)
+            assert np.array_equal(s.view(np.uint32), z["ref_scores_idf1"][q].view(np.uint32))
+
+
+def test_int8_bit_exact(golden_dir):
+    z = np.load(os.path.join(golden_dir, "int8.npz"))
+    for fn in (np_oracle.int8_dot_batch, c_oracle.int8_dot_batch):
+        s = fn(z["q8"], z["d8"], z["qscale"], z["dscale"])
+        assert np.array_equal(s.view(np.uint32), z["ref_sims"].view(np.uint32))
+    q, sc = np_oracle.quantize_rows(z["emb"])
+    assert np.array_equal(q, z["d8"][:len(q)]) and np.array_equal(sc, z["dscale"][:len(q)])
+
+
+def test_service_text_matches_reference(golden_dir):
+    with open(os.path.join(golden_dir, "service_text.json")) as f:
+        g = json.load(f)
+    ix = np_oracle.build_text_index(g["corpus"])
+    assert len(ix["vocabulary"]) == g["meta"]["vocab_size"]
+    assert ix["avgdl"] == g["meta"]["avgdl"]
+    assert len(ix["data"]) == g["meta"]["nnz"]
+    assert sorted(ix["vocabulary"], key=ix["vocabulary"].get)[:8] == g["meta"]["vocab_head"]
+    assert float(np.sum(ix["idf"].astype(np.float64))) == g["meta"]["idf_sum"]
+    got = np_oracle.search_bm25_text(ix, g["queries"], top_k=10)
+    for qid, ref in g["ref_top10"].items():
+        mine = got[qid]
+        # score multiset is pinned exactly; ids wherever the reference's tie order is not in play
+        assert sorted(mine.values(), reverse=True) == sorted(ref.values(), reverse=True), qid
+        if len(set(ref.values())) == len(ref) and len(ref) < 10:
+            assert list(mine) == list(ref), qid
+    assert g["ref_top10"]["blank"] == {} and g["ref_top10"]["oov"] == {}
+    got500 = np_oracle.search_bm25_text(ix, {k: g["queries"][k] for k in g["ref_top500"]}, top_k=500)
+    for qid, ref in g["ref_top500"].items():
+        assert got500[qid].keys() == ref.keys()
+        for d, v in ref.items():
+            assert got500[qid][d] == v
