@@ -1,0 +1,162 @@
+/*
+ * b200ret.h -- C ABI of libb200ret.so: the B200 (sm_100a) retrieval scoring hot path.
+ *
+ * Every entry point replaces one piece of the reference's Python/Numba hot path (paths relative
+ * to the reference root); INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ *   b2r_index_build        <- the CSR half of RetrievalService.build_bm25_index
+ *                             (rag_system/core/retrieval.py:176-190): takes the doc-major CSR the
+ *                             reference builds and lays it out term-major in HBM.
+ *   b2r_search_batch       <- simd_bm25_score + fast_topk_selection as called per query by
+ *                             RetrievalService._score_bm25_query (retrieval.py:256-273), batched;
+ *                             with an impact-kind index it is simd_tfidf_score + top-k
+ *                             (rag_system/pipeline/evaluate_rag_pipeline.py:95-121, :391-399).
+ *   b2r_search_batch_host  <- same, host buffers in / host buffers out (the plugin-facing call).
+ *   b2r_topk               <- fast_topk_selection (retrieval.py:79-92; retriever_registry.py:75-87;
+ *                             evaluate_rag_pipeline.py:124-159).
+ *   b2r_merge_candidates   <- no reference counterpart (the reference is single-process); merges the
+ *                             per-shard top-k lists of a doc-sharded corpus.
+ *   b2r_int8_dot_batch     <- quantized_dot_product_batch (retriever_registry.py:90-117).
+ *   b2r_int8_scan_topk     <- QuantizedEmbeddingRetriever.search's scan + argpartition
+ *                             (retriever_registry.py:495-515) without materialising [Q, N].
+ *
+ * Conventions
+ *   - Plain C types only; every pointer is a DEVICE pointer unless the name ends in _h.
+ *   - The caller owns all memory (PyTorch tensors in the Python host); the library never allocates
+ *     device memory.  Workspace sizes come from the *_workspace functions.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*) and, except for the *_host
+ *     call, nothing synchronises.
+ *   - Return value: 0 on success, negative b2r_status otherwise; b2r_last_error() gives the
+ *     thread-local message.  There is no CPU fallback anywhere in this library.
+ *   - Ranking rule everywhere: f32 score descending, then document index ascending.  A candidate
+ *     travels as a 64-bit key  (ordered_u32(score) << 32) | (0xFFFFFFFF - global_doc_index);
+ *     larger key = better rank; key 0 = "no candidate".  Global doc indices must be < 2^32 - 1.
+ */
+#ifndef B200RET_H
+#define B200RET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_VERSION 100
+#define B2R_TOPK_MAX_FAST 1024 /* larger k takes the full-sort path of b2r_topk */
+
+typedef enum b2r_status {
+    B2R_OK = 0,
+    B2R_ERR_ARG = -1,
+    B2R_ERR_CUDA = -2,
+    B2R_ERR_WORKSPACE = -3,
+    B2R_ERR_UNSUPPORTED = -4,
+    B2R_ERR_DATA = -5
+} b2r_status;
+
+typedef enum b2r_kind {
+    B2R_KIND_BM25 = 0,  /* post_val = f64 saturation factor (tf*(k1+1))/(tf+k1*(1-b+b*dl/avgdl)) */
+    B2R_KIND_IMPACT = 1 /* post_val = f32 weight; score = sum f64(f32(f32(w*qw)*idf)) */
+} b2r_kind;
+
+/* Term-major index over one shard of documents.  A plain descriptor: the buffers belong to the
+ * caller.  Postings of term t that fall in document tile T (tile_docs consecutive local docs) are
+ * post_doc/post_val[blk_ptr[t*n_tiles+T] .. blk_ptr[t*n_tiles+T+1]). */
+typedef struct b2r_index {
+    int64_t n_docs;      /* documents in this shard */
+    int64_t doc_id_base; /* global index of local document 0 */
+    int64_t nnz;         /* postings in this shard (< 2^32) */
+    int32_t n_vocab;
+    int32_t tile_docs;   /* power of two, 256..16384 */
+    int32_t n_tiles;     /* ceil(n_docs / tile_docs) */
+    int32_t kind;        /* b2r_kind */
+    uint32_t *post_doc;  /* [nnz] local doc index */
+    void *post_val;      /* [nnz] f64 (BM25) or f32 (IMPACT) */
+    uint32_t *blk_ptr;   /* [n_vocab * n_tiles + 1] */
+} b2r_index;
+
+typedef struct b2r_index_sizes {
+    size_t post_doc_bytes;
+    size_t post_val_bytes;
+    size_t blk_ptr_bytes;
+    size_t scratch_bytes; /* build-time scratch */
+} b2r_index_sizes;
+
+int b2r_version(void);
+const char *b2r_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long b2r_launch_count(void);
+
+/* Byte sizes of the buffers of an index with these dimensions (no device access). */
+int b2r_index_sizes_for(int64_t nnz, int64_t n_docs, int32_t n_vocab, int32_t tile_docs, int32_t kind,
+                        b2r_index_sizes *out);
+
+/* Fill ix->post_doc / post_val / blk_ptr (caller-allocated, sizes from b2r_index_sizes_for) from a
+ * doc-major CSR resident on the device: tf f32[nnz], indices i32[nnz] (any order inside a row),
+ * indptr i64[n_docs+1], doc_len f32[n_docs] (ignored for IMPACT).  k1, b, avgdl as the reference
+ * holds them (retrieval.py:116-117,190).  Enqueues only; *status_flag (device int32, inside scratch)
+ * is checked by b2r_index_build_status after the caller synchronises. */
+int b2r_index_build(const b2r_index *ix, const float *tf, const int32_t *indices, const int64_t *indptr,
+                    const float *doc_len, double k1, double b, double avgdl, void *scratch,
+                    size_t scratch_bytes, void *stream);
+/* Synchronises the stream and reports malformed input (term id out of range) found by the build. */
+int b2r_index_build_status(const void *scratch, void *stream);
+
+/* Workspace for b2r_search_batch: *min_bytes lets it run one query at a time, *full_bytes lets it
+ * score all n_queries in one pass; anything in between is used as given. */
+int b2r_search_workspace(const b2r_index *ix, int32_t n_queries, int32_t k, size_t *min_bytes,
+                         size_t *full_bytes);
+
+/* Batched scoring + selection.  Queries are CSR-style: terms of query q are
+ * q_terms[q_ptr[q]..q_ptr[q+1]) (ascending, unique, weights > 0 -- the positive entries of the
+ * reference's dense query_tf vector), idf is f32[n_vocab].
+ *   scores_out : optional f32[n_queries, scores_stride] dense scores (stride >= n_tiles*tile_docs,
+ *                multiple of 4); entries [n_docs, stride) of a row are padding.
+ *   keys_out   : optional u64[n_queries, k] ranked candidate keys (needs k >= 1).
+ *   idx_out/val_out : optional i64 / f32 [n_queries, k]; -1 / -inf where fewer than k docs exist.
+ */
+int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
+                     const float *idf, int32_t n_queries, int32_t k, float *scores_out, int64_t scores_stride,
+                     uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* Same with HOST query buffers and HOST outputs (pinned memory recommended): copies the queries in,
+ * runs b2r_search_batch, copies idx/val/keys out and synchronises the stream.  `workspace` must hold
+ * b2r_search_host_extra_bytes(n_queries, n_query_terms, k) more bytes than the device call needs. */
+size_t b2r_search_host_extra_bytes(int32_t n_queries, int64_t n_query_terms, int32_t k);
+int b2r_search_batch_host(const b2r_index *ix, const int32_t *q_ptr_h, const int32_t *q_terms_h,
+                          const float *q_weights_h, const float *idf, int32_t n_queries, int32_t k,
+                          uint64_t *keys_out_h, int64_t *idx_out_h, float *val_out_h, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/* Row-wise top-k of f32 scores [n_rows, n] (row stride in elements).  Global index of element j of a
+ * row is doc_id_base + j.  val_out holds scores[idx] bit-for-bit.  k <= n required (the caller
+ * clamps, as the reference does with `k >= n`). */
+int b2r_topk_workspace(int64_t n_rows, int64_t n, int32_t k, size_t *bytes);
+int b2r_topk(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k, int64_t doc_id_base,
+             uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace, size_t workspace_bytes,
+             void *stream);
+
+/* Merge the ranked candidate keys of n_parts shards, gathered as u64[n_parts, n_queries, k], into
+ * the global top-k per query.  workspace >= n_queries*k*8 bytes when keys_out is NULL. */
+int b2r_merge_candidates(const uint64_t *gathered, int32_t n_parts, int32_t n_queries, int32_t k,
+                         uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/* Decode ranked keys into (global doc index, f32 score). */
+int b2r_decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, void *stream);
+
+/* INT8 dense similarity, out f32[n_q, n_docs] = f32((f64(dot) * f64(qscale[q])) * f64(dscale[d])). */
+int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,
+                       const float *q_scale, const float *d_scale, float *out, void *stream);
+/* Exhaustive INT8 scan with fused per-query top-k (never materialises [n_q, n_docs]). */
+int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim, int32_t k, size_t *bytes);
+int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,
+                       const float *q_scale, const float *d_scale, int32_t k, int64_t doc_id_base,
+                       uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RET_H */

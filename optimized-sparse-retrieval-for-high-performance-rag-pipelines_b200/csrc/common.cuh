@@ -1,0 +1,98 @@
+// Shared device/host helpers of libb200ret (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200ret.h"
+
+namespace b2r {
+
+void set_error(const char *fmt, ...);
+
+
+#define B2R_CHECK_ARG(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            b2r::set_error(__VA_ARGS__);    \
+            return B2R_ERR_ARG;             \
+        }                                   \
+    } while (0)
+
+#define B2R_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            b2r::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return B2R_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// every kernel launch of the library goes through this macro; the counter backs b2r_launch_count()
+extern unsigned long long g_launches;
+#define B2R_LAUNCH_CHECK()               \
+    do {                                 \
+        ++b2r::g_launches;               \
+        B2R_CUDA(cudaGetLastError());    \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Candidate keys.  Ranking rule: f32 score descending (-0.0 == +0.0, NaN last), then global doc
+// index ascending.  key = ordered_u32(score) << 32 | (0xFFFFFFFF - index); larger key ranks first;
+// 0 is the "no candidate" sentinel (every real key is >= 1 because index < 2^32 - 1).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ord_f32(float f) {
+    uint32_t u = __float_as_uint(f);
+    if (f != f) return 0u;
+    if (f == 0.0f) u = 0u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+__device__ __forceinline__ uint64_t make_key(uint32_t o, uint32_t gid) {
+    return ((uint64_t)o << 32) | (uint64_t)(0xFFFFFFFFu - gid);
+}
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// In-shared-memory bitonic sort, descending, of P (power of two) u64 keys by the whole CTA.
+// Ends with a __syncthreads().
+template <int THREADS>
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t *arr, int P) {
+    const int tid = threadIdx.x;
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (P >> 1); i += THREADS) {
+                int pos = 2 * i - (i & (stride - 1));
+                uint64_t a = arr[pos], b = arr[pos + stride];
+                bool desc = ((pos & size) == 0);
+                if (desc ? (a < b) : (a > b)) {
+                    arr[pos] = b;
+                    arr[pos + stride] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// internal entry points shared between translation units
+int topk_keys_rows(const uint64_t *keys_in, int64_t n_rows, int64_t n, int64_t row_stride, int64_t piece_len,
+                   int64_t piece_stride, int32_t k, uint64_t *keys_out, void *ws, size_t ws_bytes,
+                   cudaStream_t st);
+int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k,
+                     int64_t doc_id_base, uint64_t *keys_out, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k);
+int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
+                int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st);
+
+}  // namespace b2r

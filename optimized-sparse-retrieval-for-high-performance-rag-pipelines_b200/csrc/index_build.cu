@@ -1,0 +1,259 @@
+// Term-major index builder: doc-major CSR (what RetrievalService.build_bm25_index produces,
+// rag_system/core/retrieval.py:176-184) -> tile-partitioned posting lists in HBM.
+//
+//   pass 1  count   : histogram of postings per (term, doc tile)            atomics on blk_ptr
+//   pass 2  scan    : exclusive prefix sum over the n_vocab*n_tiles table   3 kernels, in place
+//   pass 3  scatter : write (local doc, value) into its block               atomics on the cursor
+//
+// The BM25 posting value is the query-independent factor of the reference formula
+// (retrieval.py:58,70-72), evaluated with the same f64 operations in the same order:
+//   u = (tf * (k1 + 1.0)) / (tf + k1 * (1.0 - b + b * dl / avgdl))
+// so that scoring is  acc += (idf * u) * qtf  -- bit-identical to the reference's per-posting term.
+// The order of postings inside one (term, tile) block is unspecified (atomic cursor); results do not
+// depend on it because a document occurs at most once per term list.
+#include "common.cuh"
+
+namespace b2r {
+
+constexpr int BLD_THREADS = 256;
+
+// scratch layout: [0] int32 status flag (non-zero = malformed input), then scan partials
+struct BuildScratch {
+    int32_t *flag;
+    uint32_t *chunk_sums;
+    size_t n_chunks;
+};
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_CHUNK = BLD_THREADS * SCAN_ITEMS;  // 4096 table entries per CTA
+
+static size_t scan_chunks_for(size_t n_entries) { return (n_entries + SCAN_CHUNK - 1) / SCAN_CHUNK; }
+
+__global__ void __launch_bounds__(BLD_THREADS)
+build_count_kernel(const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr, int64_t n_docs,
+                   int32_t n_vocab, int n_tiles, int tile_shift, uint32_t *__restrict__ cnt /* table + 1 */,
+                   int32_t *__restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t d = warp; d < n_docs; d += n_warps) {
+        const int64_t beg = indptr[d], end = indptr[d + 1];
+        const int64_t tile = d >> tile_shift;
+        for (int64_t p = beg + lane; p < end; p += 32) {
+            int32_t t = indices[p];
+            if (t < 0 || t >= n_vocab) {
+                *flag = 1;
+                continue;
+            }
+            atomicAdd(&cnt[(size_t)t * n_tiles + tile], 1u);
+        }
+    }
+}
+
+// --- exclusive scan over `n` u32 entries, in place ---------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < (BLD_THREADS / 32) ? warp_sums[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < (BLD_THREADS / 32)) warp_sums[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    return warp_sums[wid] + inc - v;
+}
+
+__global__ void __launch_bounds__(BLD_THREADS)
+scan_reduce_kernel(const uint32_t *__restrict__ tab, size_t n, uint32_t *__restrict__ chunk_sums) {
+    __shared__ uint32_t ws[BLD_THREADS / 32];
+    __shared__ uint32_t tot;
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) s += tab[base + i];
+    block_exclusive_scan(s, ws, &tot);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(BLD_THREADS)
+scan_chunks_kernel(uint32_t *__restrict__ chunk_sums, size_t n_chunks) {
+    __shared__ uint32_t ws[BLD_THREADS / 32];
+    __shared__ uint32_t tot;
+    uint32_t carry = 0;
+    for (size_t base = 0; base < n_chunks; base += BLD_THREADS) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < n_chunks ? chunk_sums[i] : 0;
+        uint32_t ex = block_exclusive_scan(v, ws, &tot);
+        if (i < n_chunks) chunk_sums[i] = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BLD_THREADS)
+scan_apply_kernel(uint32_t *__restrict__ tab, size_t n, const uint32_t *__restrict__ chunk_sums) {
+    __shared__ uint32_t ws[BLD_THREADS / 32];
+    __shared__ uint32_t tot;
+    const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? tab[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t run = block_exclusive_scan(s, ws, &tot) + chunk_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) tab[base + i] = run;
+        run += v[i];
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BLD_THREADS)
+build_scatter_kernel(const float *__restrict__ tf, const int32_t *__restrict__ indices,
+                     const int64_t *__restrict__ indptr, const float *__restrict__ doc_len, int64_t n_docs,
+                     int32_t n_vocab, int n_tiles, int tile_shift, double k1, double b, double avgdl,
+                     uint32_t *__restrict__ cursor /* table + 1 */, uint32_t *__restrict__ post_doc,
+                     void *__restrict__ post_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double k1p1 = __dadd_rn(k1, 1.0);
+    const double one_m_b = __dsub_rn(1.0, b);
+    for (int64_t d = warp; d < n_docs; d += n_warps) {
+        const int64_t beg = indptr[d], end = indptr[d + 1];
+        const int64_t tile = d >> tile_shift;
+        double norm = 0.0;
+        if (KIND == B2R_KIND_BM25) {
+            // k1 * (1.0 - b + b * dl / avgdl)  == k1 * ((1.0 - b) + ((b * dl) / avgdl))
+            double dl = (double)doc_len[d];
+            norm = __dmul_rn(k1, __dadd_rn(one_m_b, __ddiv_rn(__dmul_rn(b, dl), avgdl)));
+        }
+        for (int64_t p = beg + lane; p < end; p += 32) {
+            int32_t t = indices[p];
+            if (t < 0 || t >= n_vocab) continue;
+            uint32_t slot = atomicAdd(&cursor[(size_t)t * n_tiles + tile], 1u);
+            post_doc[slot] = (uint32_t)d;
+            float f = tf[p];
+            if (KIND == B2R_KIND_BM25) {
+                double fd = (double)f;
+                static_cast<double *>(post_val)[slot] = __ddiv_rn(__dmul_rn(fd, k1p1), __dadd_rn(fd, norm));
+            } else {
+                static_cast<float *>(post_val)[slot] = f;
+            }
+        }
+    }
+}
+
+static int tile_shift_of(int tile_docs) {
+    int s = 0;
+    while ((1 << s) < tile_docs) ++s;
+    return s;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+extern "C" int b2r_index_sizes_for(int64_t nnz, int64_t n_docs, int32_t n_vocab, int32_t tile_docs, int32_t kind,
+                                   b2r_index_sizes *out) {
+    B2R_CHECK_ARG(out, "b2r_index_sizes_for: null out");
+    B2R_CHECK_ARG(nnz >= 0 && nnz < 0xFFFF0000ll, "index: nnz=%lld must be < 2^32 - 65536 per shard", (long long)nnz);
+    B2R_CHECK_ARG(n_docs >= 1 && n_docs < 0xFFFFFFFFll && n_vocab >= 1, "index: bad n_docs/n_vocab");
+    B2R_CHECK_ARG(tile_docs >= 256 && tile_docs <= 16384 && (tile_docs & (tile_docs - 1)) == 0,
+                  "index: tile_docs=%d must be a power of two in [256,16384]", tile_docs);
+    B2R_CHECK_ARG(kind == B2R_KIND_BM25 || kind == B2R_KIND_IMPACT, "index: unknown kind %d", kind);
+    int64_t n_tiles = (n_docs + tile_docs - 1) / tile_docs;
+    B2R_CHECK_ARG(n_tiles <= 65535, "index: %lld doc tiles exceed 65535; raise tile_docs", (long long)n_tiles);
+    size_t entries = (size_t)n_vocab * (size_t)n_tiles + 1;
+    out->post_doc_bytes = align_up((size_t)(nnz > 0 ? nnz : 1) * 4, 256);
+    out->post_val_bytes = align_up((size_t)(nnz > 0 ? nnz : 1) * (kind == B2R_KIND_BM25 ? 8 : 4), 256);
+    out->blk_ptr_bytes = align_up(entries * 4, 256);
+    out->scratch_bytes = 256 + align_up(scan_chunks_for(entries) * 4, 256);
+    return B2R_OK;
+}
+
+extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32_t *indices, const int64_t *indptr,
+                               const float *doc_len, double k1, double b, double avgdl, void *scratch,
+                               size_t scratch_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->blk_ptr, "b2r_index_build: index buffers not set");
+    B2R_CHECK_ARG(indptr && scratch, "b2r_index_build: null input");
+    B2R_CHECK_ARG(ix->nnz == 0 || (tf && indices), "b2r_index_build: null postings");
+    B2R_CHECK_ARG(ix->kind != B2R_KIND_BM25 || doc_len, "b2r_index_build: BM25 index needs doc_len");
+    b2r_index_sizes sz;
+    int rc = b2r_index_sizes_for(ix->nnz, ix->n_docs, ix->n_vocab, ix->tile_docs, ix->kind, &sz);
+    if (rc) return rc;
+    B2R_CHECK_ARG(ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs, "b2r_index_build: n_tiles mismatch");
+    if (scratch_bytes < sz.scratch_bytes) {
+        set_error("b2r_index_build: scratch too small (%zu < %zu)", scratch_bytes, sz.scratch_bytes);
+        return B2R_ERR_WORKSPACE;
+    }
+    if (ix->kind == B2R_KIND_BM25)
+        B2R_CHECK_ARG(avgdl > 0.0 || ix->nnz == 0, "b2r_index_build: avgdl must be positive");
+
+    const size_t entries = (size_t)ix->n_vocab * (size_t)ix->n_tiles + 1;
+    const size_t n_chunks = scan_chunks_for(entries);
+    int32_t *flag = static_cast<int32_t *>(scratch);
+    uint32_t *chunk_sums = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) + 256);
+    const int shift = tile_shift_of(ix->tile_docs);
+
+    B2R_CUDA(cudaMemsetAsync(scratch, 0, 256, st));
+    B2R_CUDA(cudaMemsetAsync(ix->blk_ptr, 0, entries * 4, st));
+    // one warp per document row; enough CTAs to fill the machine several times over
+    int64_t warps_needed = ix->n_docs;
+    int64_t blocks = (warps_needed * 32 + BLD_THREADS - 1) / BLD_THREADS;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) blocks = 1;
+    // counts go to table[1 + i] so that, after the exclusive scan and the scatter's atomic cursor
+    // walk, table[i] = start and table[i + 1] = end of block i.
+    build_count_kernel<<<(unsigned)blocks, BLD_THREADS, 0, st>>>(indices, indptr, ix->n_docs, ix->n_vocab, ix->n_tiles,
+                                                                shift, ix->blk_ptr + 1, flag);
+    B2R_LAUNCH_CHECK();
+    const size_t n_scan = entries - 1;
+    if (n_scan > 0) {
+        scan_reduce_kernel<<<(unsigned)n_chunks, BLD_THREADS, 0, st>>>(ix->blk_ptr + 1, n_scan, chunk_sums);
+        B2R_LAUNCH_CHECK();
+        scan_chunks_kernel<<<1, BLD_THREADS, 0, st>>>(chunk_sums, scan_chunks_for(n_scan));
+        B2R_LAUNCH_CHECK();
+        scan_apply_kernel<<<(unsigned)scan_chunks_for(n_scan), BLD_THREADS, 0, st>>>(ix->blk_ptr + 1, n_scan, chunk_sums);
+        B2R_LAUNCH_CHECK();
+    }
+    if (ix->kind == B2R_KIND_BM25)
+        build_scatter_kernel<B2R_KIND_BM25><<<(unsigned)blocks, BLD_THREADS, 0, st>>>(
+            tf, indices, indptr, doc_len, ix->n_docs, ix->n_vocab, ix->n_tiles, shift, k1, b, avgdl, ix->blk_ptr + 1,
+            ix->post_doc, ix->post_val);
+    else
+        build_scatter_kernel<B2R_KIND_IMPACT><<<(unsigned)blocks, BLD_THREADS, 0, st>>>(
+            tf, indices, indptr, doc_len, ix->n_docs, ix->n_vocab, ix->n_tiles, shift, k1, b, avgdl, ix->blk_ptr + 1,
+            ix->post_doc, ix->post_val);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
+extern "C" int b2r_index_build_status(const void *scratch, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t flag = 0;
+    B2R_CUDA(cudaMemcpyAsync(&flag, scratch, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    B2R_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+        set_error("b2r_index_build: a term id in `indices` is outside [0, n_vocab)");
+        return B2R_ERR_DATA;
+    }
+    return B2R_OK;
+}

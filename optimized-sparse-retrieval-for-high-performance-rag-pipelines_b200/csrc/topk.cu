@@ -1,0 +1,424 @@
+// Per-row top-k selection (reference: fast_topk_selection, rag_system/core/retrieval.py:79-92).
+//
+// Streaming threshold select: a CTA streams one segment of a row through registers, keeps the
+// current k best keys sorted at the front of a 2048-entry shared array and appends only elements
+// that beat the running k-th best ("tau").  Nothing is ever fully sorted: only the k best plus the
+// few hundred pending candidates go through a bitonic network.  The first sub-chunk bootstraps tau
+// from per-thread group maxima (the k-th largest of >= k disjoint group maxima is a lower bound of
+// the k-th largest element), so the usual cost per element is one load and one 64-bit compare and
+// the kernel is HBM-bound: 4 bytes per score.
+//
+// Ranking rule and key layout: common.cuh.
+#include "common.cuh"
+
+namespace b2r {
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_SN = 2048;       // shared key array (16 KB): [0,k) best, [k,SN) pending candidates
+constexpr int TK_FLUSH_AT = 256;  // merge pending candidates into the best list at this fill level
+constexpr int TK_TARGET_CTAS = 148 * 8;
+
+// Merge the c pending candidates into the sorted best list; returns the new threshold.
+__device__ __forceinline__ uint64_t tk_flush(uint64_t *arr, int *cnt, int k, int c, uint64_t tau) {
+    const int tid = threadIdx.x;
+    const int total = k + c;
+    int P = 2;
+    while (P < total) P <<= 1;
+    for (int i = total + tid; i < P; i += TK_THREADS) arr[i] = 0;
+    __syncthreads();
+    bitonic_sort_desc<TK_THREADS>(arr, P);
+    uint64_t kth = arr[k - 1];
+    if (tid == 0) *cnt = 0;
+    __syncthreads();
+    return kth > tau ? kth : tau;
+}
+
+// Element j of row r lives at  (j / piece_len) * piece_stride + r * row_stride + j % piece_len
+// (piece_len >= n for an ordinary [rows, n] array; piece_len = k for shard-gathered [W, Q, k]).
+template <bool KEYS_IN, int E>
+__global__ void __launch_bounds__(TK_THREADS)
+topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict__ keys_in, int64_t n,
+                   int64_t row_stride, int64_t piece_len, int64_t piece_stride, uint32_t id_base, int k,
+                   int64_t seg_len, uint64_t *__restrict__ out) {
+    __shared__ uint64_t arr[TK_SN];
+    __shared__ int cnt;
+    constexpr int SUB = TK_THREADS * E;
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x;
+    const int seg = blockIdx.y, n_segs = gridDim.y;
+    const int64_t seg_beg = (int64_t)seg * seg_len;
+    const int64_t seg_end = min(n, seg_beg + seg_len);
+    const int CAP = TK_SN - k;
+
+    for (int i = tid; i < TK_SN; i += TK_THREADS) arr[i] = 0;
+    if (tid == 0) cnt = 0;
+    __syncthreads();
+
+    uint64_t tau = 0;
+    bool need_boot = (seg_end - seg_beg) > (int64_t)CAP;
+    const float *rp = KEYS_IN ? nullptr : scores + row * row_stride;
+    const bool vec_ok = !KEYS_IN && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) && ((seg_len & 3) == 0);
+    const bool single_piece = piece_len >= n;
+
+    for (int64_t base = seg_beg; base < seg_end; base += SUB) {
+        uint64_t key[E];
+        if (KEYS_IN) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int64_t j = base + (int64_t)e * TK_THREADS + tid;
+                uint64_t v = 0;
+                if (j < seg_end) {
+                    int64_t off = single_piece ? (row * row_stride + j)
+                                               : ((j / piece_len) * piece_stride + row * row_stride + (j % piece_len));
+                    v = keys_in[off];
+                }
+                key[e] = v;
+            }
+        } else if (vec_ok && base + SUB <= seg_end) {
+#pragma unroll
+            for (int v = 0; v < E / 4; ++v) {
+                int64_t j = base + ((int64_t)v * TK_THREADS + tid) * 4;
+                float4 f = ldg_stream_f4(rp + j);
+                uint32_t g = id_base + (uint32_t)j;
+                key[4 * v + 0] = make_key(ord_f32(f.x), g + 0);
+                key[4 * v + 1] = make_key(ord_f32(f.y), g + 1);
+                key[4 * v + 2] = make_key(ord_f32(f.z), g + 2);
+                key[4 * v + 3] = make_key(ord_f32(f.w), g + 3);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int64_t j = base + (int64_t)e * TK_THREADS + tid;
+                key[e] = (j < seg_end) ? make_key(ord_f32(__ldg(rp + j)), id_base + (uint32_t)j) : 0ull;
+            }
+        }
+
+        if (need_boot) {  // uniform; first sub-chunk of a long segment
+            need_boot = false;
+            int G = 1;
+            while (G * TK_THREADS < k) G <<= 1;  // k <= 1024 -> G <= 4
+            uint64_t m[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int e = 0; e < E; ++e) m[e & 3] = key[e] > m[e & 3] ? key[e] : m[e & 3];
+            if (G <= 2) {
+                m[0] = m[0] > m[2] ? m[0] : m[2];
+                m[1] = m[1] > m[3] ? m[1] : m[3];
+            }
+            if (G == 1) m[0] = m[0] > m[1] ? m[0] : m[1];
+            arr[tid] = m[0];
+            if (G >= 2) arr[TK_THREADS + tid] = m[1];
+            if (G >= 4) {
+                arr[2 * TK_THREADS + tid] = m[2];
+                arr[3 * TK_THREADS + tid] = m[3];
+            }
+            __syncthreads();
+            bitonic_sort_desc<TK_THREADS>(arr, G * TK_THREADS);
+            uint64_t t0 = arr[k - 1];
+            __syncthreads();
+            tau = t0 ? t0 - 1 : 0;
+            for (int i = tid; i < G * TK_THREADS; i += TK_THREADS) arr[i] = 0;
+            __syncthreads();
+        }
+
+        uint32_t pend = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (key[e] > tau) pend |= 1u << e;
+        if (!__syncthreads_or(pend != 0)) continue;
+
+        while (true) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if ((pend >> e) & 1u) {
+                    int slot = atomicAdd(&cnt, 1);
+                    if (slot < CAP) {
+                        arr[k + slot] = key[e];
+                        pend &= ~(1u << e);
+                    }
+                }
+            }
+            __syncthreads();
+            const int c = cnt;
+            __syncthreads();
+            const bool over = c > CAP;
+            if (over || c >= TK_FLUSH_AT) {
+                tau = tk_flush(arr, &cnt, k, over ? CAP : c, tau);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (((pend >> e) & 1u) && key[e] <= tau) pend &= ~(1u << e);
+            }
+            if (!over) break;
+        }
+    }
+
+    __syncthreads();
+    const int c = cnt;
+    __syncthreads();
+    if (c > 0) tk_flush(arr, &cnt, k, c, tau);
+    uint64_t *o = out + (row * n_segs + seg) * (int64_t)k;
+    for (int i = tid; i < k; i += TK_THREADS) o[i] = arr[i];
+}
+
+// ------------------------------------------------------------------------------------------ plan
+struct TkPlan {
+    int n_segs;
+    int64_t seg_len;
+};
+
+static TkPlan tk_plan(int64_t n_rows, int64_t n, int sub) {
+    int64_t max_segs = (n + sub - 1) / sub;
+    if (max_segs < 1) max_segs = 1;
+    int64_t want = (TK_TARGET_CTAS + n_rows - 1) / n_rows;
+    if (want < 1) want = 1;
+    int64_t segs = want < max_segs ? want : max_segs;
+    int64_t seg_len = (n + segs - 1) / segs;
+    seg_len = (seg_len + sub - 1) / sub * sub;
+    if (seg_len < sub) seg_len = sub;
+    segs = (n + seg_len - 1) / seg_len;
+    if (segs < 1) segs = 1;
+    TkPlan p;
+    p.n_segs = (int)segs;
+    p.seg_len = seg_len;
+    return p;
+}
+
+constexpr int TK_E_SCORES = 16;
+constexpr int TK_E_KEYS = 8;
+
+static size_t tk_keys_ws(int64_t n_rows, int64_t n, int32_t k) {
+    size_t total = 0;
+    while (true) {
+        TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_KEYS);
+        if (p.n_segs == 1) return total;
+        total += align_up((size_t)n_rows * p.n_segs * k * 8, 256);
+        n = (int64_t)p.n_segs * k;
+    }
+}
+
+size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k) {
+    TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_SCORES);
+    if (p.n_segs == 1) return 256;
+    size_t l1 = align_up((size_t)n_rows * p.n_segs * k * 8, 256);
+    return l1 + tk_keys_ws(n_rows, (int64_t)p.n_segs * k, k) + 256;
+}
+
+int topk_keys_rows(const uint64_t *keys_in, int64_t n_rows, int64_t n, int64_t row_stride, int64_t piece_len,
+                   int64_t piece_stride, int32_t k, uint64_t *keys_out, void *ws, size_t ws_bytes,
+                   cudaStream_t st) {
+    if (n_rows == 0) return B2R_OK;
+    B2R_CHECK_ARG(k >= 1 && k <= B2R_TOPK_MAX_FAST, "top-k: k=%d outside [1,%d]", k, B2R_TOPK_MAX_FAST);
+    char *wp = static_cast<char *>(ws);
+    size_t left = ws_bytes;
+    while (true) {
+        TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_KEYS);
+        uint64_t *dst = keys_out;
+        if (p.n_segs > 1) {
+            size_t need = align_up((size_t)n_rows * p.n_segs * k * 8, 256);
+            if (need > left) {
+                set_error("top-k merge: workspace too small (%zu > %zu)", need, left);
+                return B2R_ERR_WORKSPACE;
+            }
+            dst = reinterpret_cast<uint64_t *>(wp);
+            wp += need;
+            left -= need;
+        }
+        dim3 grid((unsigned)n_rows, (unsigned)p.n_segs);
+        topk_stream_kernel<true, TK_E_KEYS><<<grid, TK_THREADS, 0, st>>>(nullptr, keys_in, n, row_stride, piece_len,
+                                                                         piece_stride, 0u, k, p.seg_len, dst);
+        B2R_LAUNCH_CHECK();
+        if (p.n_segs == 1) return B2R_OK;
+        keys_in = dst;
+        n = (int64_t)p.n_segs * k;
+        row_stride = n;
+        piece_len = n;
+        piece_stride = 0;
+    }
+}
+
+int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k,
+                     int64_t doc_id_base, uint64_t *keys_out, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (n_rows == 0) return B2R_OK;
+    B2R_CHECK_ARG(k >= 1 && k <= B2R_TOPK_MAX_FAST, "top-k: k=%d outside [1,%d]", k, B2R_TOPK_MAX_FAST);
+    B2R_CHECK_ARG(doc_id_base >= 0 && doc_id_base + n < 0xFFFFFFFFll, "top-k: global doc index exceeds 2^32-2");
+    B2R_CHECK_ARG(n_rows < 0x7FFFFFFFll, "top-k: too many rows");
+    TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_SCORES);
+    uint64_t *dst = keys_out;
+    char *wp = static_cast<char *>(ws);
+    size_t left = ws_bytes;
+    if (p.n_segs > 1) {
+        size_t need = align_up((size_t)n_rows * p.n_segs * k * 8, 256);
+        if (need > left) {
+            set_error("top-k: workspace too small (%zu > %zu)", need, left);
+            return B2R_ERR_WORKSPACE;
+        }
+        dst = reinterpret_cast<uint64_t *>(wp);
+        wp += need;
+        left -= need;
+    }
+    dim3 grid((unsigned)n_rows, (unsigned)p.n_segs);
+    topk_stream_kernel<false, TK_E_SCORES><<<grid, TK_THREADS, 0, st>>>(scores, nullptr, n, row_stride, n, 0,
+                                                                         (uint32_t)doc_id_base, k, p.seg_len, dst);
+    B2R_LAUNCH_CHECK();
+    if (p.n_segs == 1) return B2R_OK;
+    int64_t n2 = (int64_t)p.n_segs * k;
+    return topk_keys_rows(dst, n_rows, n2, n2, n2, 0, k, keys_out, wp, left, st);
+}
+
+// ------------------------------------------------------------------------------------------ decode
+__global__ void decode_keys_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t *__restrict__ idx_out,
+                                   float *__restrict__ val_out, const float *__restrict__ scores,
+                                   int64_t row_stride, int k, int64_t doc_id_base) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    int64_t idx = -1;
+    float val = __int_as_float(0xff800000);  // -inf
+    if (key != 0) {
+        uint32_t gid = 0xFFFFFFFFu - (uint32_t)key;
+        idx = (int64_t)gid;
+        val = scores ? scores[(i / k) * row_stride + (idx - doc_id_base)] : unord_f32((uint32_t)(key >> 32));
+    }
+    if (idx_out) idx_out[i] = idx;
+    if (val_out) val_out[i] = val;
+}
+
+int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
+                int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st) {
+    if (n == 0 || (!idx_out && !val_out)) return B2R_OK;
+    int threads = 256;
+    int64_t blocks = (n + threads - 1) / threads;
+    decode_keys_kernel<<<(unsigned)blocks, threads, 0, st>>>(keys, n, idx_out, val_out, scores, row_stride,
+                                                            k > 0 ? k : 1, doc_id_base);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
+// ------------------------------------------------------------------------------------------ full sort (k > 1024)
+__global__ void make_keys_kernel(const float *__restrict__ scores, int64_t n, int64_t P, uint32_t id_base,
+                                 uint64_t *__restrict__ keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    keys[i] = i < n ? make_key(ord_f32(scores[i]), id_base + (uint32_t)i) : 0ull;
+}
+
+__global__ void bitonic_global_step_kernel(uint64_t *__restrict__ keys, int64_t P, int64_t size, int64_t stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (P >> 1)) return;
+    int64_t pos = 2 * i - (i & (stride - 1));
+    uint64_t a = keys[pos], b = keys[pos + stride];
+    bool desc = ((pos & size) == 0);
+    if (desc ? (a < b) : (a > b)) {
+        keys[pos] = b;
+        keys[pos + stride] = a;
+    }
+}
+
+static int64_t pow2_ceil(int64_t x) {
+    int64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+static int full_sort_row(const float *scores, int64_t n, int64_t doc_id_base, uint64_t *buf, cudaStream_t st) {
+    int64_t P = pow2_ceil(n < 2 ? 2 : n);
+    int threads = 256;
+    make_keys_kernel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(scores, n, P, (uint32_t)doc_id_base,
+                                                                                 buf);
+    B2R_LAUNCH_CHECK();
+    unsigned blocks = (unsigned)(((P >> 1) + threads - 1) / threads);
+    for (int64_t size = 2; size <= P; size <<= 1)
+        for (int64_t stride = size >> 1; stride > 0; stride >>= 1)
+            bitonic_global_step_kernel<<<blocks, threads, 0, st>>>(buf, P, size, stride);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+extern "C" int b2r_topk_workspace(int64_t n_rows, int64_t n, int32_t k, size_t *bytes) {
+    B2R_CHECK_ARG(bytes && n_rows >= 0 && n >= 0 && k >= 1, "b2r_topk_workspace: bad arguments");
+    if (k <= B2R_TOPK_MAX_FAST) {
+        *bytes = topk_ws_bytes(n_rows > 0 ? n_rows : 1, n > 0 ? n : 1, k) + (size_t)n_rows * k * 8 + 256;
+    } else {
+        *bytes = (size_t)pow2_ceil(n < 2 ? 2 : n) * 8 + 256;
+    }
+    return B2R_OK;
+}
+
+extern "C" int b2r_topk(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k,
+                        int64_t doc_id_base, uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B2R_CHECK_ARG(scores && n_rows >= 0 && n >= 1 && row_stride >= n, "b2r_topk: bad shape");
+    B2R_CHECK_ARG(k >= 1 && k <= n, "b2r_topk: need 1 <= k <= n (k=%d, n=%lld)", k, (long long)n);
+    B2R_CHECK_ARG(doc_id_base >= 0 && doc_id_base + n < 0xFFFFFFFFll, "b2r_topk: global doc index exceeds 2^32-2");
+    if (n_rows == 0) return B2R_OK;
+    char *wp = static_cast<char *>(workspace);
+    size_t left = workspace_bytes;
+    if (k <= B2R_TOPK_MAX_FAST) {
+        uint64_t *keys = keys_out;
+        if (!keys) {
+            size_t need = align_up((size_t)n_rows * k * 8, 256);
+            if (need > left) {
+                set_error("b2r_topk: workspace too small");
+                return B2R_ERR_WORKSPACE;
+            }
+            keys = reinterpret_cast<uint64_t *>(wp);
+            wp += need;
+            left -= need;
+        }
+        int rc = topk_scores_rows(scores, n_rows, n, row_stride, k, doc_id_base, keys, wp, left, st);
+        if (rc) return rc;
+        return decode_keys(keys, n_rows * k, idx_out, val_out, scores, row_stride, k, doc_id_base, st);
+    }
+    // large k: sort the whole row (one row at a time; rare path: top_k > 1024)
+    size_t need = (size_t)pow2_ceil(n < 2 ? 2 : n) * 8;
+    if (need > left) {
+        set_error("b2r_topk: workspace too small for the full-sort path (%zu > %zu)", need, left);
+        return B2R_ERR_WORKSPACE;
+    }
+    uint64_t *buf = reinterpret_cast<uint64_t *>(wp);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int rc = full_sort_row(scores + r * row_stride, n, doc_id_base, buf, st);
+        if (rc) return rc;
+        if (keys_out)
+            B2R_CUDA(cudaMemcpyAsync(keys_out + r * k, buf, (size_t)k * 8, cudaMemcpyDeviceToDevice, st));
+        rc = decode_keys(buf, k, idx_out ? idx_out + r * k : nullptr, val_out ? val_out + r * k : nullptr,
+                         scores + r * row_stride, row_stride, k, doc_id_base, st);
+        if (rc) return rc;
+    }
+    return B2R_OK;
+}
+
+extern "C" int b2r_merge_candidates(const uint64_t *gathered, int32_t n_parts, int32_t n_queries, int32_t k,
+                                    uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
+                                    size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B2R_CHECK_ARG(gathered && n_parts >= 1 && n_queries >= 0 && k >= 1 && k <= B2R_TOPK_MAX_FAST,
+                  "b2r_merge_candidates: bad arguments");
+    if (n_queries == 0) return B2R_OK;
+    char *wp = static_cast<char *>(workspace);
+    size_t left = workspace_bytes;
+    uint64_t *keys = keys_out;
+    if (!keys) {
+        size_t need = align_up((size_t)n_queries * k * 8, 256);
+        if (need > left) {
+            set_error("b2r_merge_candidates: workspace too small");
+            return B2R_ERR_WORKSPACE;
+        }
+        keys = reinterpret_cast<uint64_t *>(wp);
+        wp += need;
+        left -= need;
+    }
+    int rc = topk_keys_rows(gathered, n_queries, (int64_t)n_parts * k, k, k, (int64_t)n_queries * k, k, keys, wp,
+                            left, st);
+    if (rc) return rc;
+    return decode_keys(keys, (int64_t)n_queries * k, idx_out, val_out, nullptr, 0, k, 0, st);
+}
+
+extern "C" int b2r_decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, void *stream) {
+    B2R_CHECK_ARG(keys || n == 0, "b2r_decode_keys: null keys");
+    return decode_keys(keys, n, idx_out, val_out, nullptr, 0, 1, 0, static_cast<cudaStream_t>(stream));
+}

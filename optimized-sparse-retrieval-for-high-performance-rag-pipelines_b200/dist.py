@@ -1,0 +1,91 @@
+"""Doc-sharded search across the GPUs of one box (no reference counterpart: the reference is a
+single CPU process).
+
+One process per GPU (torch.distributed, NCCL).  Rank r owns the contiguous global document range
+shard_range(n_docs, world, r); its TermMajorIndex carries doc_id_base = range start, so candidate
+keys hold GLOBAL document indices and the (score desc, doc index asc) rule is global.  idf and avgdl
+are global statistics: df is all-reduced (int64[V]) and avgdl is computed from the all-reduced
+(sum of lengths, N) -- or passed in when the caller has the full doc_lengths vector, which
+reproduces the reference's float(np.mean(f32)) bit-for-bit.  Per batch the only traffic is an
+all-gather of u64[Q, k] candidate keys followed by a merge kernel (b2r_merge_candidates).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_range", "global_statistics", "gather_candidates", "ShardedBM25"]
+
+
+def shard_range(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous split: every rank gets ceil(n/world) docs except the tail."""
+    per = (n_docs + world - 1) // world
+    lo = min(n_docs, rank * per)
+    return lo, min(n_docs, lo + per)
+
+
+def global_statistics(local_indices: np.ndarray, local_doc_lengths: np.ndarray, n_vocab: int, group=None,
+                      device: Optional[torch.device] = None):
+    """All-reduce df[V], sum(doc_len) and N over the shards.  Returns (idf f32[V], avgdl, n_docs_global)
+    with the reference's expressions (rag_system/core/retrieval.py:187-190) applied to the global
+    counts.  avgdl here is f32(sum)/N computed in f64 then rounded through f32, which equals
+    float(np.mean(f32 array)) whenever the f32 pairwise sum is exact (integer lengths, N < 2^24 * ...)."""
+    df = torch.from_numpy(np.bincount(local_indices, minlength=n_vocab).astype(np.int64))
+    tot = torch.tensor([float(np.sum(local_doc_lengths.astype(np.float64))), float(len(local_doc_lengths))],
+                       dtype=torch.float64)
+    if device is not None:
+        df, tot = df.to(device), tot.to(device)
+    if dist.is_initialized():
+        dist.all_reduce(df, group=group)
+        dist.all_reduce(tot, group=group)
+    df_h = df.cpu().numpy()
+    n_global = int(round(float(tot[1])))
+    idf = np.log((n_global - df_h + 0.5) / (df_h + 0.5)).astype(np.float32)
+    avgdl = float(np.float32(float(tot[0]) / n_global))
+    return idf, avgdl, n_global
+
+
+def gather_candidates(local_keys: torch.Tensor, group=None) -> torch.Tensor:
+    """all_gather of the [Q, k] candidate keys -> [world, Q, k]."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local_keys.unsqueeze(0)
+    out = torch.empty((world,) + tuple(local_keys.shape), dtype=local_keys.dtype, device=local_keys.device)
+    if local_keys.is_cuda:
+        dist.all_gather_into_tensor(out, local_keys.contiguous(), group=group)
+    else:   # gloo (CPU tests of the plumbing)
+        dist.all_gather(list(out.unbind(0)), local_keys.contiguous(), group=group)
+    return out
+
+
+class ShardedBM25:
+    """Holds this rank's shard and runs search -> all-gather -> merge."""
+
+    def __init__(self, shard_index, group=None):
+        self.ix = shard_index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._ws = None
+
+    def search(self, q_ptr, q_terms, q_weights, k: int):
+        from . import _abi
+        from .index import _stream_ptr
+        _idx, _val, keys = self.ix.search(q_ptr, q_terms, q_weights, k, return_keys=True)
+        if self.world == 1:
+            return _idx, _val
+        gathered = gather_candidates(keys, self.group)
+        nq = int(keys.shape[0])
+        dev = keys.device
+        idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        need = nq * k * 8 + (1 << 20)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _abi.check(_abi.lib.b2r_merge_candidates(gathered.data_ptr(), self.world, nq, k, None, idx.data_ptr(),
+                                                 val.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                                 _stream_ptr(dev)), "merge candidates")
+        return idx, val

@@ -1,0 +1,201 @@
+"""Drop-in functions with the reference's kernel signatures, running on the B200.
+
+  simd_bm25_score / simd_bm25_batch_score  <- rag_system/core/retrieval.py:41-76,
+                                              rag_system/core/retriever_registry.py:37-72
+  fast_topk_selection                      <- retrieval.py:79-92 (int64 indices),
+                                              evaluate_rag_pipeline.py:124-159 (int32: index_dtype=)
+  simd_tfidf_score                         <- rag_system/pipeline/evaluate_rag_pipeline.py:95-121
+  quantized_dot_product_batch              <- rag_system/core/retriever_registry.py:90-117
+  optimized_bm25_score / fast_topk         <- README.md:128-203 aliases (semantics of the executable
+                                              code above; k1/b/avgdl as keyword arguments)
+
+Inputs and outputs are numpy arrays like the reference's; CUDA tensors are accepted too and then
+returned.  The array-level scorers need a term-major index: it is built on the GPU on first use and
+cached on the identity of the CSR arrays (pointer, size, k1, b, avgdl), so a loop over queries --
+how the reference calls these functions -- pays the O(nnz) build once, not per query.  Mutating the
+CSR arrays in place invalidates that assumption: call clear_index_cache().
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+from .index import TermMajorIndex, _cuda_device, _stream_ptr, _to_device, queries_from_dense
+
+__all__ = ["simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
+           "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
+           "int8_scan_topk"]
+
+# key -> (index, the source arrays: holding them keeps their addresses from being reused)
+_INDEX_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_INDEX_CACHE_MAX = 2
+
+
+def clear_index_cache() -> None:
+    _INDEX_CACHE.clear()
+
+
+def _ident(a) -> tuple:
+    if isinstance(a, torch.Tensor):
+        return ("t", a.data_ptr(), tuple(a.shape), str(a.dtype))
+    a = np.asarray(a)
+    return ("n", a.__array_interface__["data"][0], a.shape, a.dtype.str)
+
+
+def _cached_index(kind, data, indices, indptr, doc_lengths, n_vocab, k1, b, avgdl) -> TermMajorIndex:
+    key = (kind, _ident(data), _ident(indices), _ident(indptr),
+           _ident(doc_lengths) if doc_lengths is not None else None, int(n_vocab), float(k1), float(b), float(avgdl))
+    hit = _INDEX_CACHE.get(key)
+    ix = hit[0] if hit is not None else None
+    if ix is None:
+        ones = np.ones(n_vocab, np.float32)   # idf is a per-call input: set below
+        ix = TermMajorIndex.from_csr(data, indices, indptr, doc_lengths, n_vocab=n_vocab, idf=ones,
+                                     avgdl=avgdl, k1=k1, b=b, kind=kind)
+        _INDEX_CACHE[key] = (ix, (data, indices, indptr, doc_lengths))
+        while len(_INDEX_CACHE) > _INDEX_CACHE_MAX:
+            _INDEX_CACHE.popitem(last=False)
+    else:
+        _INDEX_CACHE.move_to_end(key)
+    return ix
+
+
+def _n_vocab_for(query_tf, idf_weights) -> int:
+    # the reference guards `term_idx < len(query_tf)` and indexes idf_weights[term_idx]
+    return int(np.shape(query_tf)[-1])
+
+
+def simd_bm25_score(query_tf, doc_tf_data, doc_tf_indices, doc_tf_indptr, doc_lengths, idf_weights,
+                    k1: float, b: float, avgdl: float):
+    """BM25 scores f32[N] of one query (or f32[Q, N] for a [Q, V] batch of query vectors)."""
+    was_tensor = isinstance(query_tf, torch.Tensor)
+    q = query_tf.detach().cpu().numpy() if was_tensor else np.asarray(query_tf, dtype=np.float32)
+    n_vocab = _n_vocab_for(q, idf_weights)
+    ix = _cached_index("bm25", doc_tf_data, doc_tf_indices, doc_tf_indptr, doc_lengths, n_vocab, k1, b, avgdl)
+    idf = idf_weights.detach().cpu().numpy() if isinstance(idf_weights, torch.Tensor) else np.asarray(idf_weights)
+    ix.set_idf(np.asarray(idf, np.float32)[:n_vocab] if len(idf) >= n_vocab else
+               np.concatenate([idf, np.zeros(n_vocab - len(idf), np.float32)]))
+    ptr, terms, w = queries_from_dense(q)
+    s = ix.score_dense(ptr, terms, w)
+    if q.ndim == 1:
+        s = s[0]
+    return s if was_tensor else s.cpu().numpy()
+
+
+simd_bm25_batch_score = simd_bm25_score
+
+
+def simd_tfidf_score(query_tf, doc_tf_data, doc_tf_indices, doc_tf_indptr, idf_weights):
+    """Impact-weighted sparse dot  sum tf * idf * qtf  (f32 products, f64 accumulate)."""
+    was_tensor = isinstance(query_tf, torch.Tensor)
+    q = query_tf.detach().cpu().numpy() if was_tensor else np.asarray(query_tf, dtype=np.float32)
+    n_vocab = _n_vocab_for(q, idf_weights)
+    ix = _cached_index("impact", doc_tf_data, doc_tf_indices, doc_tf_indptr, None, n_vocab, 0.0, 0.0, 0.0)
+    idf = idf_weights.detach().cpu().numpy() if isinstance(idf_weights, torch.Tensor) else np.asarray(idf_weights)
+    ix.set_idf(np.asarray(idf, np.float32)[:n_vocab])
+    ptr, terms, w = queries_from_dense(q)
+    s = ix.score_dense(ptr, terms, w)
+    if q.ndim == 1:
+        s = s[0]
+    return s if was_tensor else s.cpu().numpy()
+
+
+def fast_topk_selection(scores, k: int, index_dtype=np.int64) -> Tuple[np.ndarray, np.ndarray]:
+    """k largest of scores[n], descending; ties broken by ascending index; k >= n returns all n
+    sorted.  Returns (indices, scores[indices]).  Accepts a [rows, n] batch as well."""
+    was_tensor = isinstance(scores, torch.Tensor)
+    dev = _cuda_device(scores.device if was_tensor and scores.is_cuda else None)
+    s = _to_device(scores, torch.float32, dev)
+    one_row = s.dim() == 1
+    if one_row:
+        s = s[None, :]
+    rows, n = int(s.shape[0]), int(s.shape[1])
+    k = min(int(k), n)
+    if k <= 0 or n == 0:
+        e_i, e_v = np.zeros((rows, 0), index_dtype), np.zeros((rows, 0), np.float32)
+        return (e_i[0], e_v[0]) if one_row else (e_i, e_v)
+    nbytes = C.c_size_t(0)
+    _abi.check(_abi.lib.b2r_topk_workspace(rows, n, k, C.byref(nbytes)), "top-k workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    idx = torch.empty((rows, k), dtype=torch.int64, device=dev)
+    val = torch.empty((rows, k), dtype=torch.float32, device=dev)
+    _abi.check(_abi.lib.b2r_topk(s.data_ptr(), rows, n, int(s.stride(0)), k, 0, None, idx.data_ptr(),
+                                 val.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "top-k")
+    if one_row:
+        idx, val = idx[0], val[0]
+    if was_tensor:
+        return idx, val
+    return idx.cpu().numpy().astype(index_dtype, copy=False), val.cpu().numpy()
+
+
+def quantized_dot_product_batch(queries_int8, corpus_int8, query_scales, corpus_scales):
+    """f32[Q, N] = f32((f64(int dot) * f64(qscale[q])) * f64(dscale[n]))."""
+    was_tensor = isinstance(corpus_int8, torch.Tensor)
+    dev = _cuda_device(corpus_int8.device if was_tensor and corpus_int8.is_cuda else None)
+    q8 = _to_device(queries_int8, torch.int8, dev)
+    d8 = _to_device(corpus_int8, torch.int8, dev)
+    qs = _to_device(np.asarray(query_scales).reshape(-1) if not isinstance(query_scales, torch.Tensor)
+                    else query_scales.reshape(-1), torch.float32, dev)
+    ds = _to_device(np.asarray(corpus_scales).reshape(-1) if not isinstance(corpus_scales, torch.Tensor)
+                    else corpus_scales.reshape(-1), torch.float32, dev)
+    if q8.dim() != 2 or d8.dim() != 2 or q8.shape[1] != d8.shape[1]:
+        raise ValueError("queries_int8 [Q, dim] and corpus_int8 [N, dim] must share dim")
+    if qs.numel() != q8.shape[0] or ds.numel() != d8.shape[0]:
+        raise ValueError("one scale per query row and per corpus row is required")
+    out = torch.empty((q8.shape[0], d8.shape[0]), dtype=torch.float32, device=dev)
+    _abi.check(_abi.lib.b2r_int8_dot_batch(q8.data_ptr(), q8.shape[0], d8.data_ptr(), d8.shape[0], q8.shape[1],
+                                           qs.data_ptr(), ds.data_ptr(), out.data_ptr(), _stream_ptr(dev)),
+               "int8 dot")
+    return out if was_tensor else out.cpu().numpy()
+
+
+def int8_scan_topk(queries_int8, corpus_int8, query_scales, corpus_scales, k: int, doc_id_base: int = 0):
+    """Exhaustive INT8 scan + per-query top-k without materialising [Q, N].
+    Returns CUDA tensors (idx i64[Q,k], val f32[Q,k], keys)."""
+    dev = _cuda_device(corpus_int8.device if isinstance(corpus_int8, torch.Tensor) and corpus_int8.is_cuda else None)
+    q8 = _to_device(queries_int8, torch.int8, dev)
+    d8 = _to_device(corpus_int8, torch.int8, dev)
+    qs = _to_device(query_scales, torch.float32, dev).reshape(-1)
+    ds = _to_device(corpus_scales, torch.float32, dev).reshape(-1)
+    nq, n, dim = int(q8.shape[0]), int(d8.shape[0]), int(d8.shape[1])
+    k = min(int(k), n)
+    nbytes = C.c_size_t(0)
+    _abi.check(_abi.lib.b2r_int8_scan_workspace(nq, n, dim, k, C.byref(nbytes)), "int8 scan workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    _abi.check(_abi.lib.b2r_int8_scan_topk(q8.data_ptr(), nq, d8.data_ptr(), n, dim, qs.data_ptr(), ds.data_ptr(), k,
+                                           int(doc_id_base), keys.data_ptr(), idx.data_ptr(), val.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "int8 scan")
+    return idx, val, keys
+
+
+# ----------------------------------------------------------------------------- README aliases
+def optimized_bm25_score(query_vector, doc_vectors, doc_lengths, idf_weights, *, k1: float = 1.2, b: float = 0.75,
+                         avgdl=None):
+    """README.md:129-155 alias.  `doc_vectors` is a scipy CSR matrix (or a (data, indices, indptr)
+    triple, or a dense [N, V] array); k1 / b / avgdl -- free variables in the README pseudo-code --
+    are keyword arguments; avgdl defaults to the reference's float(np.mean(doc_lengths))."""
+    if hasattr(doc_vectors, "indptr"):
+        data, indices, indptr = doc_vectors.data, doc_vectors.indices, doc_vectors.indptr
+    elif isinstance(doc_vectors, (tuple, list)) and len(doc_vectors) == 3:
+        data, indices, indptr = doc_vectors
+    else:
+        dense = np.asarray(doc_vectors, dtype=np.float32)
+        rows, cols = np.nonzero(dense)
+        data, indices = dense[rows, cols], cols.astype(np.int32)
+        indptr = np.zeros(dense.shape[0] + 1, np.int64)
+        np.cumsum(np.bincount(rows, minlength=dense.shape[0]), out=indptr[1:])
+    if avgdl is None:
+        avgdl = float(np.mean(np.asarray(doc_lengths, dtype=np.float32)))
+    return simd_bm25_score(query_vector, data, indices, indptr, doc_lengths, idf_weights, k1, b, avgdl)
+
+
+def fast_topk(scores, k: int):
+    """README.md:187-203 alias: indices of the k largest scores, best first."""
+    return fast_topk_selection(scores, k)[0]

@@ -1,0 +1,352 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the golden vectors recorded
+from the reference and against the CPU oracle on seeded inputs.  Bar: bit-exact f32 scores (tolerance
+stated in the north star: 1e-5 relative -- we hold 0 ulp) and bit-exact top-k ids under the rule
+(score desc, doc index asc)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle, np_oracle  # noqa: E402  (the checker)
+
+
+@pytest.fixture(scope="module")
+def b2r():
+    import b200ret
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    assert os.path.exists(b200ret._abi.LIB_PATH)
+    return b200ret
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _queries(z):
+    p = z["q_ptr"]
+    return [(z["q_terms"][p[i]:p[i + 1]], z["q_weights"][p[i]:p[i + 1]]) for i in range(len(p) - 1)]
+
+
+# ----------------------------------------------------------------------------------- golden: K1
+@pytest.mark.parametrize("tile_docs", [256, 1024, 4096])
+def test_bm25_scores_bit_exact_vs_reference(b2r, golden_dir, tile_docs):
+    z = np.load(os.path.join(golden_dir, "bm25_arrays.npz"))
+    ix = b2r.TermMajorIndex.from_csr(z["data"], z["indices"], z["indptr"], z["doc_lengths"], n_vocab=len(z["idf"]),
+                                     idf=z["idf"], avgdl=float(z["avgdl"]), k1=float(z["k1"]), b=float(z["b"]),
+                                     tile_docs=tile_docs)
+    s = ix.score_dense(z["q_ptr"], z["q_terms"], z["q_weights"]).cpu().numpy()
+    assert np.array_equal(_bits(s), _bits(z["ref_scores"]))
+    idx, val = ix.search(z["q_ptr"], z["q_terms"], z["q_weights"], 10)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for q in range(s.shape[0]):
+        wi, wv = np_oracle.topk_canonical(z["ref_scores"][q], 10)
+        assert np.array_equal(idx[q], wi), q
+        assert np.array_equal(_bits(val[q]), _bits(np.where(wv == 0, np.float32(0), wv))), q
+        assert np.array_equal(val[q], z["ref_top_val"][q])          # the reference's own top-k values
+
+
+def test_bm25_function_signature_drop_in(b2r, golden_dir):
+    """simd_bm25_score / simd_bm25_batch_score with the reference's positional signature, one query at a time."""
+    z = np.load(os.path.join(golden_dir, "bm25_arrays.npz"))
+    nv = len(z["idf"])
+    indptr32 = z["indptr"].astype(np.int32)
+    for q, (t, w) in enumerate(_queries(z)[:6]):
+        qtf = np_oracle.dense_query(t, w, nv)
+        s = b2r.simd_bm25_score(qtf, z["data"], z["indices"], indptr32, z["doc_lengths"], z["idf"],
+                                float(z["k1"]), float(z["b"]), float(z["avgdl"]))
+        assert s.dtype == np.float32 and s.shape == (len(indptr32) - 1,)
+        assert np.array_equal(_bits(s), _bits(z["ref_scores"][q]))
+        ti, tv = b2r.fast_topk_selection(s, 10)
+        assert ti.dtype == np.int64 and np.array_equal(tv, z["ref_top_val"][q])
+    for q, (t, w) in enumerate(_queries(z)[:4]):   # registry "tfidf" parameterisation k1=1000, b=0
+        qtf = np_oracle.dense_query(t, w, nv)
+        s = b2r.simd_bm25_batch_score(qtf, z["data"], z["indices"], indptr32, z["doc_lengths"], z["idf"], 1000.0,
+                                      0.0, float(z["avgdl"]))
+        assert np.array_equal(_bits(s), _bits(z["ref_scores_k1000"][q]))
+    s = b2r.optimized_bm25_score(np_oracle.dense_query(*_queries(z)[0], nv), (z["data"], z["indices"], z["indptr"]),
+                                 z["doc_lengths"], z["idf"], k1=float(z["k1"]), b=float(z["b"]))
+    assert np.array_equal(_bits(s), _bits(z["ref_scores"][0]))
+    b2r.clear_index_cache()
+
+
+def test_bm25_fractional_inputs(b2r, golden_dir):
+    z = np.load(os.path.join(golden_dir, "bm25_frac.npz"))
+    ix = b2r.TermMajorIndex.from_csr(z["data"], z["indices"], z["indptr"], z["doc_lengths"], n_vocab=len(z["idf"]),
+                                     idf=z["idf"], avgdl=float(z["avgdl"]), k1=float(z["k1"]), b=float(z["b"]),
+                                     tile_docs=512)
+    s = ix.score_dense(z["q_ptr"], z["q_terms"], z["q_weights"]).cpu().numpy()
+    assert np.array_equal(_bits(s), _bits(z["ref_scores"]))
+
+
+# ----------------------------------------------------------------------------------- golden: K3, K4
+def test_tfidf_bit_exact_vs_reference(b2r, golden_dir):
+    z = np.load(os.path.join(golden_dir, "tfidf_arrays.npz"))
+    nv = len(z["idf"])
+    ix = b2r.TermMajorIndex.from_csr(z["data"], z["indices"], z["indptr"], n_vocab=nv, idf=z["idf"], kind="impact",
+                                     tile_docs=256)
+    s = ix.score_dense(z["q_ptr"], z["q_terms"], z["q_weights"]).cpu().numpy()
+    assert np.array_equal(_bits(s), _bits(z["ref_scores"]))
+    ix.set_idf(np.ones(nv, np.float32))
+    s = ix.score_dense(z["q_ptr"], z["q_terms"], z["q_weights"]).cpu().numpy()
+    assert np.array_equal(_bits(s), _bits(z["ref_scores_idf1"]))
+    t, w = _queries(z)[3]
+    s1 = b2r.simd_tfidf_score(np_oracle.dense_query(t, w, nv), z["data"], z["indices"], z["indptr"].astype(np.int32),
+                              z["idf"])
+    assert np.array_equal(_bits(s1), _bits(z["ref_scores"][3]))
+    b2r.clear_index_cache()
+
+
+def test_int8_bit_exact_vs_reference(b2r, golden_dir):
+    z = np.load(os.path.join(golden_dir, "int8.npz"))
+    s = b2r.quantized_dot_product_batch(z["q8"], z["d8"], z["qscale"], z["dscale"])
+    assert np.array_equal(_bits(s), _bits(z["ref_sims"]))
+    idx, val, _ = b2r.int8_scan_topk(z["q8"], z["d8"], z["qscale"], z["dscale"], 20)
+    for q in range(len(z["q8"])):
+        wi, wv = np_oracle.topk_canonical(z["ref_sims"][q], 20)
+        assert np.array_equal(idx[q].cpu().numpy(), wi) and np.array_equal(_bits(val[q].cpu().numpy()), _bits(wv))
+
+
+def test_int8_odd_shapes(b2r):
+    rng = np.random.default_rng(5)
+    for nq, n, dim in [(1, 1, 16), (3, 130, 48), (33, 257, 768), (5, 64, 100)]:
+        q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+        d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
+        qs = rng.random(nq).astype(np.float32) + 0.01
+        ds = rng.random(n).astype(np.float32) + 0.01
+        got = b2r.quantized_dot_product_batch(q8, d8, qs, ds)
+        assert np.array_equal(_bits(got), _bits(np_oracle.int8_dot_batch(q8, d8, qs, ds))), (nq, n, dim)
+
+
+# ----------------------------------------------------------------------------------- golden + edge: K2
+def test_topk_reference_cases(b2r, golden_dir):
+    z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
+    for name in ("normal", "uniform", "zipfian", "bimodal", "k_ge_n", "big"):
+        s, k = z[f"{name}_scores"], int(z[f"{name}_k"])
+        idx, val = b2r.fast_topk_selection(s, k)
+        wi, wv = np_oracle.topk_canonical(s, k)
+        assert np.array_equal(idx, wi) and np.array_equal(_bits(val), _bits(wv)), name
+        assert np.array_equal(val, z[f"{name}_ref_val"]), name      # the reference's values
+        assert np.array_equal(b2r.fast_topk(s, k), wi)
+
+
+def test_topk_edge_cases(b2r):
+    s = np.array([1.0, 2.0, 2.0, -0.0, 0.0, np.nan, 2.0, 1.0], np.float32)
+    idx, val = b2r.fast_topk_selection(s, 8)
+    assert idx.tolist() == [1, 2, 6, 0, 7, 3, 4, 5]
+    assert np.array_equal(_bits(val), _bits(s[idx]))                # -0.0 and NaN come back bit-for-bit
+    assert b2r.fast_topk_selection(s, 2)[0].tolist() == [1, 2]
+    assert b2r.fast_topk_selection(s, 100)[0].tolist() == [1, 2, 6, 0, 7, 3, 4, 5]      # k >= n: all, sorted
+    assert b2r.fast_topk_selection(np.zeros(1, np.float32), 1)[0].tolist() == [0]
+    i32, _ = b2r.fast_topk_selection(s, 3, index_dtype=np.int32)    # pipeline variant returns int32
+    assert i32.dtype == np.int32
+    z = np.zeros(100_000, np.float32)                               # all ties: lowest indices win
+    assert b2r.fast_topk_selection(z, 17)[0].tolist() == list(range(17))
+    asc = np.arange(300_000, dtype=np.float32)                      # ascending: every element beats the threshold
+    assert b2r.fast_topk_selection(asc, 5)[0].tolist() == [299999, 299998, 299997, 299996, 299995]
+    neg = -np.arange(70_000, dtype=np.float32) - 1                  # all negative
+    assert b2r.fast_topk_selection(neg, 3)[0].tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize("n,k", [(5000, 1), (4097, 10), (100_000, 100), (1_000_003, 10), (1_000_003, 1000),
+                                 (50_000, 1024), (3000, 2000), (70_000, 5000)])
+def test_topk_random_with_ties(b2r, n, k):
+    rng = np.random.default_rng(n + k)
+    s = np.round(rng.gamma(2.0, 2.0, n), 1).astype(np.float32)      # heavy ties
+    s[rng.integers(0, n, n // 50)] *= -1
+    idx, val = b2r.fast_topk_selection(s, k)
+    wi, wv = np_oracle.topk_canonical(s, k)
+    assert np.array_equal(idx, wi)
+    assert np.array_equal(_bits(val), _bits(wv))
+
+
+def test_topk_batched_rows(b2r):
+    rng = np.random.default_rng(11)
+    s = rng.normal(0, 1, (37, 20_011)).astype(np.float32)
+    idx, val = b2r.fast_topk_selection(torch.from_numpy(s).cuda(), 50)
+    for r in range(s.shape[0]):
+        wi, wv = np_oracle.topk_canonical(s[r], 50)
+        assert np.array_equal(idx[r].cpu().numpy(), wi) and np.array_equal(val[r].cpu().numpy(), wv)
+
+
+# ----------------------------------------------------------------------------------- oracle on seeded inputs
+def _oracle_topk(ix_args, q_ptr, q_terms, q_w, k):
+    data, indices, indptr, dl, idf, k1, b, avgdl = ix_args
+    return c_oracle.bm25_search_batch(q_ptr, q_terms, q_w, len(idf), data, indices, indptr, dl, idf, k1, b, avgdl, k)
+
+
+@pytest.mark.parametrize("tile_docs,k", [(256, 10), (4096, 10), (4096, 100), (16384, 10)])
+def test_bm25_search_vs_oracle_medium(b2r, tile_docs, k):
+    from b200ret import synthetic as S
+    n_docs, n_vocab = 50_000 + 37, 20_000
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 60, seed=1)
+    dl[::1000] = 0; indptr = indptr.copy()                          # (lengths only: rows keep their postings)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab)
+    avgdl = b2r.reference_avgdl(dl)
+    q_ptr, q_terms, q_w = S.zipf_queries(96, n_vocab, seed=2)
+    u_ptr, u_terms, u_w = S.zipf_queries(32, n_vocab, seed=3, uniform=True)       # rare-term stress set
+    q_ptr = np.concatenate([q_ptr, u_ptr[1:] + q_ptr[-1]]).astype(np.int32)
+    q_terms = np.concatenate([q_terms, u_terms]); q_w = np.concatenate([q_w, u_w * 2])
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl,
+                                     tile_docs=tile_docs)
+    idx, val = ix.search(q_ptr, q_terms, q_w, k)
+    wi, wv = _oracle_topk((data, indices, indptr, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, k)
+    assert np.array_equal(idx.cpu().numpy(), wi)
+    assert np.array_equal(_bits(val.cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
+    hi, hv = ix.search_host(q_ptr, q_terms, q_w, k)                 # host-buffer C-ABI call
+    assert np.array_equal(hi, wi) and np.array_equal(_bits(hv), _bits(val.cpu().numpy()))
+
+
+def test_bm25_edge_queries(b2r):
+    from b200ret import synthetic as S
+    n_docs, n_vocab = 3000, 500
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 20, seed=4)
+    keep = indices != 7                                             # term 7 never occurs: empty posting list
+    rows = np.repeat(np.arange(n_docs), np.diff(indptr))[keep]
+    data, indices = data[keep], indices[keep]
+    indptr = np.zeros(n_docs + 1, np.int64); np.cumsum(np.bincount(rows, minlength=n_docs), out=indptr[1:])
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    long_q = np.arange(0, 100, dtype=np.int32)                      # > 32 terms: several staging passes
+    q_ptr, q_terms, q_w = b2r.pack_queries([([], []), ([7], [1.0]), (long_q, np.ones(100)), ([0], [3.0]),
+                                            ([499, 7, 3], [1, 1, 2])])
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=256)
+    s = ix.score_dense(q_ptr, q_terms, q_w).cpu().numpy()
+    for q in range(len(q_ptr) - 1):
+        qtf = np_oracle.dense_query(q_terms[q_ptr[q]:q_ptr[q + 1]], q_w[q_ptr[q]:q_ptr[q + 1]], n_vocab)
+        want = c_oracle.bm25_scores(qtf, data, indices, indptr, dl, idf, 1.2, 0.75, avgdl)
+        assert np.array_equal(_bits(s[q]), _bits(want)), q
+    assert not s[0].any() and not s[1].any()
+    idx, val = ix.search(q_ptr, q_terms, q_w, 5)
+    assert idx[0].tolist() == [0, 1, 2, 3, 4] and val[0].tolist() == [0.0] * 5       # all-zero scores: lowest ids
+    with pytest.raises(ValueError):
+        b2r.TermMajorIndex.from_csr(data, indices + 1000, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+
+
+def test_sharded_merge_equals_single_index(b2r):
+    """3 doc shards with global idf/avgdl on one GPU + b2r_merge_candidates == one index over everything."""
+    from b200ret import synthetic as S
+    from b200ret.dist import shard_range
+    n_docs, n_vocab, k = 30_011, 8000, 100
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 40, seed=8)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    q_ptr, q_terms, q_w = S.zipf_queries(64, n_vocab, seed=9)
+    full = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=1024)
+    fi, fv = full.search(q_ptr, q_terms, q_w, k)
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(n_docs, 3, r)
+        s, e = indptr[lo], indptr[hi]
+        sh = b2r.TermMajorIndex.from_csr(data[s:e], indices[s:e], indptr[lo:hi + 1] - s, dl[lo:hi], n_vocab=n_vocab,
+                                         idf=idf, avgdl=avgdl, doc_id_base=lo, tile_docs=1024)
+        parts.append(sh.search(q_ptr, q_terms, q_w, k, return_keys=True)[2])
+    gathered = torch.stack(parts).contiguous()
+    nq = gathered.shape[1]
+    mi = torch.empty((nq, k), dtype=torch.int64, device="cuda"); mv = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    ws = torch.empty(nq * k * 8 + (1 << 20), dtype=torch.uint8, device="cuda")
+    lib = b2r._abi.lib
+    b2r._abi.check(lib.b2r_merge_candidates(gathered.data_ptr(), 3, nq, k, None, mi.data_ptr(), mv.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), int(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(mi, fi) and torch.equal(mv, fv)
+    wi, _ = _oracle_topk((data, indices, indptr, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, k)
+    assert np.array_equal(mi.cpu().numpy(), wi)
+
+
+# ----------------------------------------------------------------------------------- service level
+def test_service_text_api_vs_reference(b2r, golden_dir, tmp_path):
+    with open(os.path.join(golden_dir, "service_text.json")) as f:
+        g = json.load(f)
+    path = tmp_path / "docs.idx"
+    with pytest.raises(FileNotFoundError):
+        b2r.RetrievalService(path)
+    b2r.MemoryIndex(path, create=True).close()
+    with b2r.RetrievalService(path) as svc:
+        with pytest.raises(ValueError, match="not built"):
+            svc.search_bm25({"q": "x"})
+        with pytest.raises(ValueError, match="Empty corpus"):
+            svc.build_bm25_index({})
+        svc.build_bm25_index(g["corpus"])
+        m = g["meta"]
+        assert len(svc.vocabulary) == m["vocab_size"] and svc.avgdl == m["avgdl"] and svc.corpus_tf.nnz == m["nnz"]
+        assert float(np.sum(svc.idf_weights.astype(np.float64))) == m["idf_sum"]
+        assert sorted(svc.get_stats().keys()) == m["stats_keys"]
+        got = svc.search_bm25(g["queries"], top_k=10)
+        ix = np_oracle.build_text_index(g["corpus"])
+        want = np_oracle.search_bm25_text(ix, g["queries"], top_k=10)
+        assert list(got) == list(g["queries"])
+        for qid in g["queries"]:
+            assert list(got[qid].items()) == list(want[qid].items()), qid            # ids + scores + order
+            ref = g["ref_top10"][qid]
+            assert sorted(got[qid].values(), reverse=True) == sorted(ref.values(), reverse=True), qid
+        assert got["blank"] == {} and got["oov"] == {}
+        n_cached = len(svc.query_cache)
+        again = svc.search_bm25(g["queries"], top_k=10)                              # served from the cache
+        assert again == got and len(svc.query_cache) == n_cached
+        got500 = svc.search_bm25({k: g["queries"][k] for k in g["ref_top500"]}, top_k=500)   # top_k > n_docs
+        for qid, ref in g["ref_top500"].items():
+            assert got500[qid] == ref, qid
+        svc.k1 = 0.9                                                                  # attribute change -> re-layout
+        changed = svc.search_bm25({"q": g["queries"]["query_0"] + " "}, top_k=5)
+        want2 = np_oracle.search_bm25_text(ix, {"q": g["queries"]["query_0"]}, top_k=5, k1=0.9)
+        assert list(changed["q"].items()) == list(want2["q"].items())
+        svc.clear_cache()
+        assert svc.get_stats()["query_cache_size"] == 0
+
+
+def test_registry_plugin_shape(b2r, golden_dir):
+    with open(os.path.join(golden_dir, "service_text.json")) as f:
+        g = json.load(f)
+
+    class Registry:                                   # stand-in with the reference's register/create contract
+        _r = {}
+        @classmethod
+        def register(cls, name, klass): cls._r[name] = klass
+        @classmethod
+        def create(cls, cfg): return cls._r[cfg["type"]](method=cfg.get("method", "bm25"))
+    b2r.register_with(Registry)
+    r = Registry.create({"type": "bm25_b200"})
+    r.build_index_from_corpus(g["corpus"])
+    out = r.search({"a": g["queries"]["query_1"]}, top_k=10)
+    assert sorted(out["a"].values(), reverse=True) == sorted(g["ref_top10"]["query_1"].values(), reverse=True)
+
+
+# ----------------------------------------------------------------------------------- full size (C2) properties
+def test_full_size_1m_docs_properties(b2r):
+    """BASELINE config 2 shape (1M docs x 100K vocab, 1024 queries, top-10): spot-check 6 queries against
+    the oracle, and check size-independent properties on all 1024: descending order, values equal the dense
+    score at the returned index, sharded == unsharded."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab, k = 1_000_000, 100_000, 10
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 60)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    q_ptr, q_terms, q_w = S.zipf_queries(1024, n_vocab)
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+    idx, val, keys = ix.search(q_ptr, q_terms, q_w, k, return_keys=True)
+    torch.cuda.synchronize()
+    ku = keys.cpu().numpy().view(np.uint64)
+    assert bool((val[:, :-1] >= val[:, 1:]).all()) and bool((ku[:, :-1] > ku[:, 1:]).all())
+    sub = slice(0, 6)
+    wi, wv = _oracle_topk((data, indices, indptr, dl, idf, 1.2, 0.75, avgdl), q_ptr[:7], q_terms[:q_ptr[6]],
+                          q_w[:q_ptr[6]], k)
+    assert np.array_equal(idx[sub].cpu().numpy(), wi) and np.array_equal(_bits(val[sub].cpu().numpy()), _bits(wv))
+    dense = ix.score_dense(q_ptr[:9], q_terms[:q_ptr[8]], q_w[:q_ptr[8]])
+    assert torch.equal(torch.gather(dense, 1, idx[:8]), val[:8])
+    # two shards + merge == whole
+    half = n_docs // 2
+    parts = []
+    for lo, hi in ((0, half), (half, n_docs)):
+        s, e = indptr[lo], indptr[hi]
+        sh = b2r.TermMajorIndex.from_csr(data[s:e], indices[s:e], indptr[lo:hi + 1] - s, dl[lo:hi], n_vocab=n_vocab,
+                                         idf=idf, avgdl=avgdl, doc_id_base=lo)
+        parts.append(sh.search(q_ptr, q_terms, q_w, k, return_keys=True)[2])
+        del sh
+    g = torch.stack(parts).contiguous()
+    mi = torch.empty_like(idx); mv = torch.empty_like(val)
+    ws = torch.empty(1 << 22, dtype=torch.uint8, device="cuda")
+    b2r._abi.check(b2r._abi.lib.b2r_merge_candidates(g.data_ptr(), 2, 1024, k, None, mi.data_ptr(), mv.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(),
+                                                     int(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(mi, idx) and torch.equal(mv, val)
