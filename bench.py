@@ -51,10 +51,11 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(name):
+def make_workload(name, n_queries=None):
     from b200ret import synthetic as S
     import b200ret
     n_docs, n_vocab, mean_len, n_q, k, desc = WORKLOADS[name]
+    n_q = n_queries or n_q
     data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, mean_len)
     idf = b200ret.reference_idf(indices, n_docs, n_vocab)
     avgdl = b200ret.reference_avgdl(dl)
@@ -85,7 +86,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     from oracle import c_oracle
-    w = make_workload(args.workload)
+    w = make_workload(args.workload, args.n_queries)
     cores = c_oracle.num_threads()
     # size the per-step sample so that a step takes ~1.5 s
     rate, dt = cpu_reference_rate(w, 2)
@@ -179,7 +180,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    w = make_workload(args.workload)
+    w = make_workload(args.workload, args.n_queries)
     n_docs, k = w["n_docs"], w["k"]
     lo, hi = shard_range(n_docs, world, rank)
     s, e = w["indptr"][lo], w["indptr"][hi]
@@ -326,6 +327,7 @@ def main():
     ap.add_argument("--tile-docs", type=int, default=4096)
     ap.add_argument("--check", type=int, default=4, help="queries checked against the oracle after timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-queries", type=int, default=None, help="override the batch size (profiling only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -12,6 +12,23 @@
 
 namespace b2r {
 
+// posting streams are read once per CTA: keep them out of L1 (the accumulators own the SM's L1/smem pipe)
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 constexpr int SC_THREADS = 256;
 constexpr int SC_TERMS = 32;  // query terms staged per pass
 
@@ -55,26 +72,27 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
                 uint32_t p = beg + tid;
                 // 4 independent posting loads in flight per thread
                 for (; p + 3 * SC_THREADS < end; p += 4 * SC_THREADS) {
-                    uint32_t d0 = __ldg(post_doc + p), d1 = __ldg(post_doc + p + SC_THREADS);
-                    uint32_t d2 = __ldg(post_doc + p + 2 * SC_THREADS), d3 = __ldg(post_doc + p + 3 * SC_THREADS);
-                    double u0 = __ldg(pv + p), u1 = __ldg(pv + p + SC_THREADS);
-                    double u2 = __ldg(pv + p + 2 * SC_THREADS), u3 = __ldg(pv + p + 3 * SC_THREADS);
+                    uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + SC_THREADS);
+                    uint32_t d2 = ld_stream_u32(post_doc + p + 2 * SC_THREADS);
+                    uint32_t d3 = ld_stream_u32(post_doc + p + 3 * SC_THREADS);
+                    double u0 = ld_stream_f64(pv + p), u1 = ld_stream_f64(pv + p + SC_THREADS);
+                    double u2 = ld_stream_f64(pv + p + 2 * SC_THREADS), u3 = ld_stream_f64(pv + p + 3 * SC_THREADS);
                     acc[d0 - doc0] = __dadd_rn(acc[d0 - doc0], __dmul_rn(__dmul_rn(w_idf, u0), w_q));
                     acc[d1 - doc0] = __dadd_rn(acc[d1 - doc0], __dmul_rn(__dmul_rn(w_idf, u1), w_q));
                     acc[d2 - doc0] = __dadd_rn(acc[d2 - doc0], __dmul_rn(__dmul_rn(w_idf, u2), w_q));
                     acc[d3 - doc0] = __dadd_rn(acc[d3 - doc0], __dmul_rn(__dmul_rn(w_idf, u3), w_q));
                 }
                 for (; p < end; p += SC_THREADS) {
-                    uint32_t d = __ldg(post_doc + p);
-                    double u = __ldg(pv + p);
+                    uint32_t d = ld_stream_u32(post_doc + p);
+                    double u = ld_stream_f64(pv + p);
                     acc[d - doc0] = __dadd_rn(acc[d - doc0], __dmul_rn(__dmul_rn(w_idf, u), w_q));
                 }
             } else {
                 const float *__restrict__ pv = static_cast<const float *>(post_val_);
                 const float w_idf = t_idf[j], w_q = t_qw[j];
                 for (uint32_t p = beg + tid; p < end; p += SC_THREADS) {
-                    uint32_t d = __ldg(post_doc + p);
-                    float w = __ldg(pv + p);
+                    uint32_t d = ld_stream_u32(post_doc + p);
+                    float w = ld_stream_f32(pv + p);
                     // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens: see oracle/np_oracle.py
                     float c = __fmul_rn(__fmul_rn(w, w_q), w_idf);
                     acc[d - doc0] = __dadd_rn(acc[d - doc0], (double)c);

@@ -74,22 +74,40 @@ topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict_
                 }
                 key[e] = v;
             }
-        } else if (vec_ok && base + SUB <= seg_end) {
-#pragma unroll
-            for (int v = 0; v < E / 4; ++v) {
-                int64_t j = base + ((int64_t)v * TK_THREADS + tid) * 4;
-                float4 f = ldg_stream_f4(rp + j);
-                uint32_t g = id_base + (uint32_t)j;
-                key[4 * v + 0] = make_key(ord_f32(f.x), g + 0);
-                key[4 * v + 1] = make_key(ord_f32(f.y), g + 1);
-                key[4 * v + 2] = make_key(ord_f32(f.z), g + 2);
-                key[4 * v + 3] = make_key(ord_f32(f.w), g + 3);
-            }
         } else {
+            // scores stay f32 in registers; the common case (nothing beats the threshold) costs one
+            // FSETP per element.  Keys are only built for sub-chunks that hold a candidate.
+            float f[E];
+            const bool vec = vec_ok && base + SUB <= seg_end;
+            if (vec) {
+#pragma unroll
+                for (int v = 0; v < E / 4; ++v) {
+                    float4 x = ldg_stream_f4(rp + base + ((int64_t)v * TK_THREADS + tid) * 4);
+                    f[4 * v + 0] = x.x;
+                    f[4 * v + 1] = x.y;
+                    f[4 * v + 2] = x.z;
+                    f[4 * v + 3] = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    int64_t j = base + (int64_t)e * TK_THREADS + tid;
+                    f[e] = (j < seg_end) ? __ldg(rp + j) : __int_as_float(0x7fc00000);  // NaN = absent
+                }
+            }
+            const uint32_t tau_hi = (uint32_t)(tau >> 32);
+            if (!need_boot && tau_hi != 0) {
+                const float tau_f = unord_f32(tau_hi);  // an element can only pass if score >= tau_f
+                bool any = false;
+#pragma unroll
+                for (int e = 0; e < E; ++e) any |= (f[e] >= tau_f);
+                if (!__syncthreads_or(any)) continue;
+            }
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                int64_t j = base + (int64_t)e * TK_THREADS + tid;
-                key[e] = (j < seg_end) ? make_key(ord_f32(__ldg(rp + j)), id_base + (uint32_t)j) : 0ull;
+                int64_t j = vec ? base + ((int64_t)(e >> 2) * TK_THREADS + tid) * 4 + (e & 3)
+                                : base + (int64_t)e * TK_THREADS + tid;
+                key[e] = (j < seg_end) ? make_key(ord_f32(f[e]), id_base + (uint32_t)j) : 0ull;
             }
         }
 

@@ -222,8 +222,11 @@ def test_bm25_edge_queries(b2r):
     assert not s[0].any() and not s[1].any()
     idx, val = ix.search(q_ptr, q_terms, q_w, 5)
     assert idx[0].tolist() == [0, 1, 2, 3, 4] and val[0].tolist() == [0.0] * 5       # all-zero scores: lowest ids
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match="outside"):
         b2r.TermMajorIndex.from_csr(data, indices + 1000, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+    dup = indices.copy(); dup[indptr[5] + 1] = dup[indptr[5]]       # row 5 lists one term twice
+    with pytest.raises(ValueError, match="twice"):
+        b2r.TermMajorIndex.from_csr(data, dup, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=256)
 
 
 def test_sharded_merge_equals_single_index(b2r):
