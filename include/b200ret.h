@@ -61,7 +61,13 @@ typedef enum b2r_kind {
 
 /* Term-major index over one shard of documents.  A plain descriptor: the buffers belong to the
  * caller.  Postings of term t that fall in document tile T (tile_docs consecutive local docs) are
- * post_doc/post_val[blk_ptr[t*n_tiles+T] .. blk_ptr[t*n_tiles+T+1]). */
+ * post_doc/post_val[blk_ptr[t*n_tiles+T] .. blk_ptr[t*n_tiles+T+1]), ordered by doc index.
+ * Terms that average >= B2R_DENSE_MIN_PER_TILE postings per tile ("dense" terms) additionally get
+ * a row of sub-tile offsets (B2R_SUBTILES sub-tiles of tile_docs/B2R_SUBTILES docs per tile):
+ * postings of dense term t in sub-tile S are [dense_ptr[r*(n_tiles*8+1)+S], dense_ptr[...+S+1])
+ * with r = dense_id[t]; the scorer gives every warp one sub-tile and never needs a CTA barrier. */
+#define B2R_SUBTILES 8
+#define B2R_DENSE_MIN_PER_TILE 64
 typedef struct b2r_index {
     int64_t n_docs;      /* documents in this shard */
     int64_t doc_id_base; /* global index of local document 0 */
@@ -73,6 +79,10 @@ typedef struct b2r_index {
     uint32_t *post_doc;  /* [nnz] local doc index */
     void *post_val;      /* [nnz] f64 (BM25) or f32 (IMPACT) */
     uint32_t *blk_ptr;   /* [n_vocab * n_tiles + 1] */
+    int32_t *dense_id;   /* [n_vocab] row of dense_ptr, or -1 */
+    uint32_t *dense_ptr; /* [n_dense_max * (n_tiles * B2R_SUBTILES + 1)] */
+    int32_t n_dense_max; /* rows allocated in dense_ptr (from b2r_index_sizes_for) */
+    int32_t reserved0;
 } b2r_index;
 
 typedef struct b2r_index_sizes {
@@ -80,6 +90,9 @@ typedef struct b2r_index_sizes {
     size_t post_val_bytes;
     size_t blk_ptr_bytes;
     size_t scratch_bytes; /* build-time scratch */
+    size_t dense_id_bytes;
+    size_t dense_ptr_bytes;
+    int64_t n_dense_max;
 } b2r_index_sizes;
 
 int b2r_version(void);

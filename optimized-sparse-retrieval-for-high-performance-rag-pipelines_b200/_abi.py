@@ -30,6 +30,10 @@ class B2RIndex(C.Structure):
         ("post_doc", C.c_void_p),
         ("post_val", C.c_void_p),
         ("blk_ptr", C.c_void_p),
+        ("dense_id", C.c_void_p),
+        ("dense_ptr", C.c_void_p),
+        ("n_dense_max", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -39,6 +43,9 @@ class B2RIndexSizes(C.Structure):
         ("post_val_bytes", C.c_size_t),
         ("blk_ptr_bytes", C.c_size_t),
         ("scratch_bytes", C.c_size_t),
+        ("dense_id_bytes", C.c_size_t),
+        ("dense_ptr_bytes", C.c_size_t),
+        ("n_dense_max", C.c_int64),
     ]
 
 

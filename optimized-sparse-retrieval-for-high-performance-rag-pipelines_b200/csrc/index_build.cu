@@ -253,6 +253,51 @@ build_order_kernel(const uint32_t *__restrict__ blk_ptr, size_t n_blocks, int n_
     }
 }
 
+// ---- pass 5: sub-tile offsets for dense terms ---------------------------------------------------
+// A term is dense when it averages >= B2R_DENSE_MIN_PER_TILE postings per tile; at most
+// nnz / (B2R_DENSE_MIN_PER_TILE * n_tiles) terms can be, which bounds the table.
+__global__ void __launch_bounds__(BLD_THREADS)
+dense_select_kernel(const uint32_t *__restrict__ blk_ptr, int32_t n_vocab, int n_tiles, uint32_t min_df,
+                    int32_t n_dense_max, int32_t *__restrict__ dense_id, int32_t *__restrict__ counter) {
+    int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vocab) return;
+    uint32_t df = blk_ptr[(size_t)(t + 1) * n_tiles] - blk_ptr[(size_t)t * n_tiles];
+    int32_t id = -1;
+    if (df >= min_df) {
+        id = atomicAdd(counter, 1);
+        if (id >= n_dense_max) id = -1;  // cannot happen (counting argument); stay safe
+    }
+    dense_id[t] = id;
+}
+
+// One warp per 4 tiles of a dense term: lane = (tile offset << 3) | sub-tile; each lane binary-searches
+// the first posting of its sub-tile in the doc-ordered block.
+__global__ void __launch_bounds__(BLD_THREADS)
+dense_fill_kernel(const uint32_t *__restrict__ blk_ptr, const uint32_t *__restrict__ post_doc,
+                  const int32_t *__restrict__ dense_id, int32_t n_vocab, int n_tiles, int tile_docs,
+                  uint32_t *__restrict__ dense_ptr) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x;
+    const int32_t id = dense_id[t];
+    if (id < 0) return;
+    const int sub_docs = tile_docs / B2R_SUBTILES;
+    const size_t row = (size_t)id * ((size_t)n_tiles * B2R_SUBTILES + 1);
+    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int T0 = warp * 4; T0 < n_tiles; T0 += n_warps * 4) {
+        const int T = T0 + (lane >> 3), s = lane & 7;
+        if (T >= n_tiles) continue;
+        uint32_t lo = blk_ptr[(size_t)t * n_tiles + T], hi = blk_ptr[(size_t)t * n_tiles + T + 1];
+        const uint32_t target = (uint32_t)T * (uint32_t)tile_docs + (uint32_t)s * (uint32_t)sub_docs;
+        while (lo < hi) {  // lower_bound(target)
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            if (post_doc[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        dense_ptr[row + (size_t)T * B2R_SUBTILES + s] = lo;
+    }
+    if (threadIdx.x == 0) dense_ptr[row + (size_t)n_tiles * B2R_SUBTILES] = blk_ptr[(size_t)(t + 1) * n_tiles];
+}
+
 static int tile_shift_of(int tile_docs) {
     int s = 0;
     while ((1 << s) < tile_docs) ++s;
@@ -278,6 +323,9 @@ extern "C" int b2r_index_sizes_for(int64_t nnz, int64_t n_docs, int32_t n_vocab,
     out->post_val_bytes = align_up((size_t)(nnz > 0 ? nnz : 1) * (kind == B2R_KIND_BM25 ? 8 : 4), 256);
     out->blk_ptr_bytes = align_up(entries * 4, 256);
     out->scratch_bytes = 256 + align_up(scan_chunks_for(entries) * 4, 256) + out->post_doc_bytes + out->post_val_bytes;
+    out->n_dense_max = nnz / ((int64_t)B2R_DENSE_MIN_PER_TILE * n_tiles) + 1;
+    out->dense_id_bytes = align_up((size_t)n_vocab * 4, 256);
+    out->dense_ptr_bytes = align_up((size_t)out->n_dense_max * ((size_t)n_tiles * B2R_SUBTILES + 1) * 4, 256);
     return B2R_OK;
 }
 
@@ -285,7 +333,8 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
                                const float *doc_len, double k1, double b, double avgdl, void *scratch,
                                size_t scratch_bytes, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->blk_ptr, "b2r_index_build: index buffers not set");
+    B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->blk_ptr && ix->dense_id && ix->dense_ptr,
+                  "b2r_index_build: index buffers not set");
     B2R_CHECK_ARG(indptr && scratch, "b2r_index_build: null input");
     B2R_CHECK_ARG(ix->nnz == 0 || (tf && indices), "b2r_index_build: null postings");
     B2R_CHECK_ARG(ix->kind != B2R_KIND_BM25 || doc_len, "b2r_index_build: BM25 index needs doc_len");
@@ -293,6 +342,7 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
     int rc = b2r_index_sizes_for(ix->nnz, ix->n_docs, ix->n_vocab, ix->tile_docs, ix->kind, &sz);
     if (rc) return rc;
     B2R_CHECK_ARG(ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs, "b2r_index_build: n_tiles mismatch");
+    B2R_CHECK_ARG(ix->n_dense_max == sz.n_dense_max, "b2r_index_build: n_dense_max mismatch");
     if (scratch_bytes < sz.scratch_bytes) {
         set_error("b2r_index_build: scratch too small (%zu < %zu)", scratch_bytes, sz.scratch_bytes);
         return B2R_ERR_WORKSPACE;
@@ -358,6 +408,17 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
                                                                               ix->tile_docs, tmp_doc, tmp_val,
                                                                               ix->post_doc, ix->post_val, flag);
         }
+        B2R_LAUNCH_CHECK();
+    }
+    {
+        int32_t *counter = flag + 1;  // scratch[4..8): number of dense terms
+        const uint32_t min_df = (uint32_t)B2R_DENSE_MIN_PER_TILE * (uint32_t)ix->n_tiles;
+        dense_select_kernel<<<(unsigned)((ix->n_vocab + BLD_THREADS - 1) / BLD_THREADS), BLD_THREADS, 0, st>>>(
+            ix->blk_ptr, ix->n_vocab, ix->n_tiles, min_df, ix->n_dense_max, ix->dense_id, counter);
+        B2R_LAUNCH_CHECK();
+        dense_fill_kernel<<<(unsigned)ix->n_vocab, BLD_THREADS, 0, st>>>(ix->blk_ptr, ix->post_doc, ix->dense_id,
+                                                                         ix->n_vocab, ix->n_tiles, ix->tile_docs,
+                                                                         ix->dense_ptr);
         B2R_LAUNCH_CHECK();
     }
     return B2R_OK;

@@ -2,12 +2,12 @@
 // (reference: simd_bm25_score, rag_system/core/retrieval.py:41-76, and simd_tfidf_score,
 //  rag_system/pipeline/evaluate_rag_pipeline.py:95-121 -- both doc-major O(nnz) scans per query).
 //
-// One CTA = one (query, doc tile).  The tile's f64 accumulators live in shared memory; the query's
-// terms are applied in ascending term id with a CTA barrier between terms, which reproduces the
-// reference's summation order (CSR rows are sorted by term id) and needs no atomics: a document
-// occurs at most once in a term's posting list.  The grid is (queries, tiles) with the query index
-// fastest, so CTAs resident at the same time work on the same doc tile and share its posting blocks
-// through L2; HBM sees each posting once per batch.
+// One CTA = one (query, doc tile), one warp = one sub-tile.  The f64 accumulators live in shared
+// memory; a warp applies the query's terms in ascending term id to its own sub-tile, which reproduces
+// the reference's summation order (CSR rows are sorted by term id) with no atomics and no CTA barrier:
+// a document occurs at most once in a term's posting list.  The grid is (queries, tiles) with the
+// query index fastest, so CTAs resident at the same time work on the same doc tile and share its
+// posting blocks through L2; HBM sees each posting once per batch.
 #include "common.cuh"
 
 namespace b2r {
@@ -29,88 +29,117 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
     return v;
 }
 
-constexpr int SC_THREADS = 256;
-constexpr int SC_TERMS = 32;  // query terms staged per pass
+constexpr int SC_THREADS = 32 * B2R_SUBTILES;  // one warp per sub-tile of the CTA's doc tile
+
+// acc[rel] += contribution of one posting (reference order of operations, no FMA contraction)
+template <int KIND>
+__device__ __forceinline__ void apply_posting(double *acc_w, uint32_t rel, double u_or_w, float w_idf, float w_q,
+                                              double w_idf64, double w_q64) {
+    if (KIND == B2R_KIND_BM25) {
+        acc_w[rel] = __dadd_rn(acc_w[rel], __dmul_rn(__dmul_rn(w_idf64, u_or_w), w_q64));
+    } else {
+        // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens: see oracle/np_oracle.py
+        float c = __fmul_rn(__fmul_rn((float)u_or_w, w_q), w_idf);
+        acc_w[rel] = __dadd_rn(acc_w[rel], (double)c);
+    }
+}
 
 template <int KIND>
+__device__ __forceinline__ double load_val(const void *post_val, uint32_t p) {
+    if (KIND == B2R_KIND_BM25) return ld_stream_f64(static_cast<const double *>(post_val) + p);
+    return (double)ld_stream_f32(static_cast<const float *>(post_val) + p);
+}
+
+// One CTA = one (query, doc tile); one WARP = one sub-tile of tile_docs/8 docs whose f64 accumulators
+// it alone touches.  A warp applies the query's terms in ascending term id to its own sub-tile, so the
+// only synchronisation is __syncwarp: no CTA barrier, no atomics, no load imbalance between warps
+// (a dense term's postings are split by sub-tile through dense_ptr; a sparse term's small block is
+// scanned by every warp, each keeping the postings that fall in its range).
+template <int KIND>
 __global__ void __launch_bounds__(SC_THREADS)
-score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val_,
-                   const uint32_t *__restrict__ blk_ptr, int n_tiles, int tile_docs,
+score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
+                   const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
+                   const uint32_t *__restrict__ dense_ptr, int n_tiles, int tile_docs,
                    const int32_t *__restrict__ q_ptr, const int32_t *__restrict__ q_terms,
                    const float *__restrict__ q_weights, const float *__restrict__ idf, int q0,
                    float *__restrict__ scores, int64_t scores_stride) {
     extern __shared__ double acc[];  // [tile_docs]
-    __shared__ uint32_t t_beg[SC_TERMS], t_end[SC_TERMS];
-    __shared__ float t_idf[SC_TERMS], t_qw[SC_TERMS];
-
-    const int tid = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = q0 + blockIdx.x;
     const int tile = blockIdx.y;
-    const uint32_t doc0 = (uint32_t)tile * (uint32_t)tile_docs;
+    const int sub = tile_docs / B2R_SUBTILES;
+    const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
+    double *acc_w = acc + w * sub;
+    const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
+    const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
 
-    for (int i = tid; i < tile_docs; i += SC_THREADS) acc[i] = 0.0;
+    for (int i = lane * 2; i < sub; i += 64) *reinterpret_cast<double2 *>(acc_w + i) = make_double2(0.0, 0.0);
+    __syncwarp();
 
     const int qs = q_ptr[q], qe = q_ptr[q + 1];
-    for (int j0 = qs; j0 < qe; j0 += SC_TERMS) {
-        const int nt = min(SC_TERMS, qe - j0);
-        __syncthreads();  // previous pass finished with the staging arrays (and acc is zeroed)
-        if (tid < nt) {
-            const int t = q_terms[j0 + tid];
-            const size_t e = (size_t)t * n_tiles + tile;
-            t_beg[tid] = blk_ptr[e];
-            t_end[tid] = blk_ptr[e + 1];
-            t_idf[tid] = idf[t];
-            t_qw[tid] = q_weights[j0 + tid];
+    for (int j0 = qs; j0 < qe; j0 += 32) {
+        const int nt = min(32, qe - j0);
+        // lane j stages term j0+j: posting range of this warp (dense) or of the whole tile block (sparse)
+        uint32_t my_beg = 0, my_end = 0;
+        float my_idf = 0.f, my_qw = 0.f;
+        int my_dense = 0;
+        if (lane < nt) {
+            const int t = q_terms[j0 + lane];
+            my_qw = q_weights[j0 + lane];
+            my_idf = idf[t];
+            const int32_t did = dense_id[t];
+            if (did >= 0) {
+                const uint32_t *row = dense_ptr + (size_t)did * dense_row + my_sub;
+                my_beg = row[0];
+                my_end = row[1];
+                my_dense = 1;
+            } else {
+                const size_t e = (size_t)t * n_tiles + tile;
+                my_beg = blk_ptr[e];
+                my_end = blk_ptr[e + 1];
+            }
         }
-        __syncthreads();
         for (int j = 0; j < nt; ++j) {
-            const uint32_t beg = t_beg[j], end = t_end[j];
-            if (beg == end) continue;  // uniform
-            if (KIND == B2R_KIND_BM25) {
-                const double *__restrict__ pv = static_cast<const double *>(post_val_);
-                const double w_idf = (double)t_idf[j], w_q = (double)t_qw[j];
-                uint32_t p = beg + tid;
-                // 4 independent posting loads in flight per thread
-                for (; p + 3 * SC_THREADS < end; p += 4 * SC_THREADS) {
-                    uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + SC_THREADS);
-                    uint32_t d2 = ld_stream_u32(post_doc + p + 2 * SC_THREADS);
-                    uint32_t d3 = ld_stream_u32(post_doc + p + 3 * SC_THREADS);
-                    double u0 = ld_stream_f64(pv + p), u1 = ld_stream_f64(pv + p + SC_THREADS);
-                    double u2 = ld_stream_f64(pv + p + 2 * SC_THREADS), u3 = ld_stream_f64(pv + p + 3 * SC_THREADS);
-                    acc[d0 - doc0] = __dadd_rn(acc[d0 - doc0], __dmul_rn(__dmul_rn(w_idf, u0), w_q));
-                    acc[d1 - doc0] = __dadd_rn(acc[d1 - doc0], __dmul_rn(__dmul_rn(w_idf, u1), w_q));
-                    acc[d2 - doc0] = __dadd_rn(acc[d2 - doc0], __dmul_rn(__dmul_rn(w_idf, u2), w_q));
-                    acc[d3 - doc0] = __dadd_rn(acc[d3 - doc0], __dmul_rn(__dmul_rn(w_idf, u3), w_q));
+            const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
+            if (beg == end) continue;  // warp-uniform
+            const int dense = __shfl_sync(full, my_dense, j);
+            const float w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
+            const double w_idf64 = (double)w_idf, w_q64 = (double)w_q;
+            if (dense) {
+                uint32_t p = beg + lane;
+                for (; p + 96 < end; p += 128) {  // 4 independent postings in flight per lane
+                    uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + 32);
+                    uint32_t d2 = ld_stream_u32(post_doc + p + 64), d3 = ld_stream_u32(post_doc + p + 96);
+                    double u0 = load_val<KIND>(post_val, p), u1 = load_val<KIND>(post_val, p + 32);
+                    double u2 = load_val<KIND>(post_val, p + 64), u3 = load_val<KIND>(post_val, p + 96);
+                    apply_posting<KIND>(acc_w, d0 - my_doc0, u0, w_idf, w_q, w_idf64, w_q64);
+                    apply_posting<KIND>(acc_w, d1 - my_doc0, u1, w_idf, w_q, w_idf64, w_q64);
+                    apply_posting<KIND>(acc_w, d2 - my_doc0, u2, w_idf, w_q, w_idf64, w_q64);
+                    apply_posting<KIND>(acc_w, d3 - my_doc0, u3, w_idf, w_q, w_idf64, w_q64);
                 }
-                for (; p < end; p += SC_THREADS) {
+                for (; p < end; p += 32) {
                     uint32_t d = ld_stream_u32(post_doc + p);
-                    double u = ld_stream_f64(pv + p);
-                    acc[d - doc0] = __dadd_rn(acc[d - doc0], __dmul_rn(__dmul_rn(w_idf, u), w_q));
+                    double u = load_val<KIND>(post_val, p);
+                    apply_posting<KIND>(acc_w, d - my_doc0, u, w_idf, w_q, w_idf64, w_q64);
                 }
             } else {
-                const float *__restrict__ pv = static_cast<const float *>(post_val_);
-                const float w_idf = t_idf[j], w_q = t_qw[j];
-                for (uint32_t p = beg + tid; p < end; p += SC_THREADS) {
-                    uint32_t d = ld_stream_u32(post_doc + p);
-                    float w = ld_stream_f32(pv + p);
-                    // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens: see oracle/np_oracle.py
-                    float c = __fmul_rn(__fmul_rn(w, w_q), w_idf);
-                    acc[d - doc0] = __dadd_rn(acc[d - doc0], (double)c);
+                for (uint32_t p = beg + lane; p < end; p += 32) {
+                    const uint32_t rel = __ldg(post_doc + p) - my_doc0;  // blocks are shared by the 8 warps: keep in L1
+                    if (rel < (uint32_t)sub) {
+                        double u = load_val<KIND>(post_val, p);
+                        apply_posting<KIND>(acc_w, rel, u, w_idf, w_q, w_idf64, w_q64);
+                    }
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
-    __syncthreads();
 
-    float *out = scores + (int64_t)blockIdx.x * scores_stride + doc0;
-    for (int i = tid * 4; i < tile_docs; i += SC_THREADS * 4) {
-        float4 v;
-        v.x = __double2float_rn(acc[i]);
-        v.y = __double2float_rn(acc[i + 1]);
-        v.z = __double2float_rn(acc[i + 2]);
-        v.w = __double2float_rn(acc[i + 3]);
-        *reinterpret_cast<float4 *>(out + i) = v;
+    float *out = scores + (int64_t)blockIdx.x * scores_stride + my_doc0;
+    for (int i = lane * 2; i < sub; i += 64) {
+        double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+        *reinterpret_cast<float2 *>(out + i) = make_float2(__double2float_rn(a.x), __double2float_rn(a.y));
     }
 }
 
@@ -122,22 +151,23 @@ static int launch_score(const b2r_index *ix, const int32_t *q_ptr, const int32_t
     if (ix->kind == B2R_KIND_BM25) {
         B2R_CUDA(cudaFuncSetAttribute(score_tiles_kernel<B2R_KIND_BM25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        score_tiles_kernel<B2R_KIND_BM25><<<grid, SC_THREADS, smem, st>>>(ix->post_doc, ix->post_val, ix->blk_ptr,
-                                                                         ix->n_tiles, ix->tile_docs, q_ptr, q_terms,
-                                                                         q_weights, idf, q0, scores, stride);
+        score_tiles_kernel<B2R_KIND_BM25><<<grid, SC_THREADS, smem, st>>>(
+            ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, q_ptr,
+            q_terms, q_weights, idf, q0, scores, stride);
     } else {
         B2R_CUDA(cudaFuncSetAttribute(score_tiles_kernel<B2R_KIND_IMPACT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_tiles_kernel<B2R_KIND_IMPACT><<<grid, SC_THREADS, smem, st>>>(ix->post_doc, ix->post_val, ix->blk_ptr,
-                                                                           ix->n_tiles, ix->tile_docs, q_ptr, q_terms,
-                                                                           q_weights, idf, q0, scores, stride);
+        score_tiles_kernel<B2R_KIND_IMPACT><<<grid, SC_THREADS, smem, st>>>(
+            ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, q_ptr,
+            q_terms, q_weights, idf, q0, scores, stride);
     }
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
 
 static int check_index(const b2r_index *ix) {
-    B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->blk_ptr, "search: index not built");
+    B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->blk_ptr && ix->dense_id && ix->dense_ptr,
+                  "search: index not built");
     B2R_CHECK_ARG(ix->tile_docs >= 256 && (ix->tile_docs & (ix->tile_docs - 1)) == 0, "search: bad tile_docs");
     B2R_CHECK_ARG(ix->n_tiles == (ix->n_docs + ix->tile_docs - 1) / ix->tile_docs && ix->n_tiles <= 65535,
                   "search: bad n_tiles");

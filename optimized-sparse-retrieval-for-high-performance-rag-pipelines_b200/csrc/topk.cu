@@ -5,8 +5,9 @@
 // that beat the running k-th best ("tau").  Nothing is ever fully sorted: only the k best plus the
 // few hundred pending candidates go through a bitonic network.  The first sub-chunk bootstraps tau
 // from per-thread group maxima (the k-th largest of >= k disjoint group maxima is a lower bound of
-// the k-th largest element), so the usual cost per element is one load and one 64-bit compare and
-// the kernel is HBM-bound: 4 bytes per score.
+// the k-th largest element).  Scores stay f32 in registers: the usual cost per element is a quarter of
+// an LDG.128 and one FMNMX, keys are only built for sub-chunks that hold a candidate, so the kernel
+// is HBM-bound: 4 bytes per score.
 //
 // Ranking rule and key layout: common.cuh.
 #include "common.cuh"
@@ -15,7 +16,6 @@ namespace b2r {
 
 constexpr int TK_THREADS = 256;
 constexpr int TK_SN = 2048;       // shared key array (16 KB): [0,k) best, [k,SN) pending candidates
-constexpr int TK_FLUSH_AT = 256;  // merge pending candidates into the best list at this fill level
 constexpr int TK_TARGET_CTAS = 148 * 8;
 
 // Merge the c pending candidates into the sorted best list; returns the new threshold.
@@ -49,6 +49,7 @@ topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict_
     const int64_t seg_beg = (int64_t)seg * seg_len;
     const int64_t seg_end = min(n, seg_beg + seg_len);
     const int CAP = TK_SN - k;
+    const int flush_at = max(1, k >> 2);  // merge pending candidates early: a fresh threshold keeps the fast path hot
 
     for (int i = tid; i < TK_SN; i += TK_THREADS) arr[i] = 0;
     if (tid == 0) cnt = 0;
@@ -96,18 +97,20 @@ topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict_
                 }
             }
             const uint32_t tau_hi = (uint32_t)(tau >> 32);
-            if (!need_boot && tau_hi != 0) {
-                const float tau_f = unord_f32(tau_hi);  // an element can only pass if score >= tau_f
-                bool any = false;
+            const bool all = need_boot || tau_hi == 0;  // no usable threshold yet: every element is a candidate
+            const float tau_f = unord_f32(tau_hi);      // an element can only pass if score >= tau_f
+            if (!all) {
+                float m = f[0];
 #pragma unroll
-                for (int e = 0; e < E; ++e) any |= (f[e] >= tau_f);
-                if (!__syncthreads_or(any)) continue;
+                for (int e = 1; e < E; ++e) m = fmaxf(m, f[e]);  // fmaxf drops NaN
+                if (!__syncthreads_or(m >= tau_f)) continue;
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 int64_t j = vec ? base + ((int64_t)(e >> 2) * TK_THREADS + tid) * 4 + (e & 3)
                                 : base + (int64_t)e * TK_THREADS + tid;
-                key[e] = (j < seg_end) ? make_key(ord_f32(f[e]), id_base + (uint32_t)j) : 0ull;
+                const bool c = (all || f[e] >= tau_f) && j < seg_end;
+                key[e] = c ? make_key(ord_f32(f[e]), id_base + (uint32_t)j) : 0ull;
             }
         }
 
@@ -159,7 +162,7 @@ topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict_
             const int c = cnt;
             __syncthreads();
             const bool over = c > CAP;
-            if (over || c >= TK_FLUSH_AT) {
+            if (over || c >= flush_at) {
                 tau = tk_flush(arr, &cnt, k, over ? CAP : c, tau);
 #pragma unroll
                 for (int e = 0; e < E; ++e)

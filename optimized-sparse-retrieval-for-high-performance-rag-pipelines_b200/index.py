@@ -8,7 +8,9 @@ libb200ret.so through the C ABI.  The doc-major scipy CSR the reference builds
 
   post_doc  u32[nnz]   local doc index of every posting, grouped by (term, doc tile)
   post_val  f64[nnz]   BM25: (tf*(k1+1))/(tf+k1*(1-b+b*dl/avgdl))   |   f32[nnz] impact weight
-  blk_ptr   u32[V*T+1] postings of (term t, tile T) are [blk_ptr[t*T_n+T], blk_ptr[t*T_n+T+1])
+  blk_ptr   u32[V*T+1] postings of (term t, tile T) are [blk_ptr[t*T_n+T], blk_ptr[t*T_n+T+1]), doc-ascending
+  dense_id  i32[V]     row of dense_ptr for terms averaging >= 64 postings per tile, else -1
+  dense_ptr u32[...]   per dense term: offsets of its postings per sub-tile (8 sub-tiles per tile)
   idf       f32[V]
 """
 from __future__ import annotations
@@ -151,6 +153,8 @@ class TermMajorIndex:
         b_["post_doc"] = torch.empty(sizes.post_doc_bytes, dtype=torch.uint8, device=dev)
         b_["post_val"] = torch.empty(sizes.post_val_bytes, dtype=torch.uint8, device=dev)
         b_["blk_ptr"] = torch.empty(sizes.blk_ptr_bytes, dtype=torch.uint8, device=dev)
+        b_["dense_id"] = torch.empty(sizes.dense_id_bytes, dtype=torch.uint8, device=dev)
+        b_["dense_ptr"] = torch.empty(sizes.dense_ptr_bytes, dtype=torch.uint8, device=dev)
         b_["idf"] = torch.from_numpy(self.idf_host).to(dev)
         scratch = torch.empty(sizes.scratch_bytes, dtype=torch.uint8, device=dev)
 
@@ -158,6 +162,7 @@ class TermMajorIndex:
         d.n_docs, d.doc_id_base, d.nnz = n_docs, self.doc_id_base, nnz
         d.n_vocab, d.tile_docs, d.n_tiles, d.kind = self.n_vocab, self.tile_docs, self.n_tiles, kind_id
         d.post_doc, d.post_val, d.blk_ptr = b_["post_doc"].data_ptr(), b_["post_val"].data_ptr(), b_["blk_ptr"].data_ptr()
+        d.dense_id, d.dense_ptr, d.n_dense_max = b_["dense_id"].data_ptr(), b_["dense_ptr"].data_ptr(), int(sizes.n_dense_max)
 
         # stage the CSR on the device (freed after the build)
         tf_d = _to_device(data, torch.float32, dev)
