@@ -111,7 +111,7 @@ def run_reference(args):
         "note": "reference is pure Python/Numba (cannot travel): timed here is oracle/bm25_oracle.c, its "
                 "loop-for-loop C+OpenMP restatement (doc-major CSR scan per query + top-k), all host threads",
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -178,6 +178,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2R_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     w = make_workload(args.workload, args.n_queries)
@@ -310,14 +311,29 @@ def run_b200(args):
             rate, dt = cpu_reference_rate(w, n_sample)
             out["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": c_oracle.num_threads(), "kind": "port",
                                    "sample": f"first {n_sample} of {nq} queries, full corpus, {dt:.1f} s of wall time"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line, on the real stdout (fd 1 is pointed at stderr while the run is in progress so
+    that library banners -- e.g. NCCL's version line -- cannot land beside it)."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    global _REAL_STDOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -331,9 +347,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
         sock = socket.socket()
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
@@ -341,6 +355,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    if args.impl == "reference":
+        return run_reference(args)
     return run_b200(args)
 
 
