@@ -133,6 +133,18 @@ int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q
                      uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* Test / profiling hook: 0 makes b2r_search_batch use the plain "score everything, then select" path
+ * instead of the fused-selection path (both are exact). */
+void b2r_set_fused_selection(int enabled);
+
+/* Profiling hooks used by bench.py: bracket the fused scoring launch of b2r_search_batch with CUDA
+ * events on its stream; b2r_profile_fused_ms returns the duration of the most recent one.
+ * b2r_fused_plan reports whether (and how) the fused path applies: *n_sample_tiles == 0 means the
+ * plain path; otherwise every tile_step-th tile forms the threshold sample. */
+int b2r_set_profiling(int enabled);
+int b2r_profile_fused_ms(float *ms, int32_t *reserved);
+int b2r_fused_plan(const b2r_index *ix, int32_t k, int32_t *n_sample_tiles, int32_t *tile_step, int32_t *cap);
+
 /* Same with HOST query buffers and HOST outputs (pinned memory recommended): copies the queries in,
  * runs b2r_search_batch, copies idx/val/keys out and synchronises the stream.  `workspace` must hold
  * b2r_search_host_extra_bytes(n_queries, n_query_terms, k) more bytes than the device call needs. */

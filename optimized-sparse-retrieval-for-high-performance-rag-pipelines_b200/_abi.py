@@ -63,6 +63,10 @@ SIGNATURES = {
     "b2r_index_build_status": (C.c_int, [_P, _P]),
     "b2r_search_workspace": (C.c_int, [_PIX, _I32, _I32, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "b2r_search_batch": (C.c_int, [_PIX, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "b2r_set_fused_selection": (None, [C.c_int]),
+    "b2r_set_profiling": (C.c_int, [C.c_int]),
+    "b2r_profile_fused_ms": (C.c_int, [C.POINTER(C.c_float), _P]),
+    "b2r_fused_plan": (C.c_int, [_PIX, _I32, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
     "b2r_search_host_extra_bytes": (_SZ, [_I32, _I64, _I32]),
     "b2r_search_batch_host": (C.c_int, [_PIX, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "b2r_topk_workspace": (C.c_int, [_I64, _I64, _I32, C.POINTER(_SZ)]),

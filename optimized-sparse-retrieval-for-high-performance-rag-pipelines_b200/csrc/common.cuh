@@ -86,12 +86,23 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t *arr, int P) {
 }
 
 // internal entry points shared between translation units
+struct TopkOpts {
+    // chunk_shift > 0: a score row is a compacted list of 2^chunk_shift-element chunks taken every
+    // chunk_stride documents: element j has index id_base + (j >> shift) * chunk_stride + (j & mask)
+    int chunk_shift = 0;
+    uint32_t chunk_stride = 0;
+    // gate != nullptr: only rows with gate[row] > gate_cap are processed, the others are left untouched
+    const int32_t *gate = nullptr;
+    int32_t gate_cap = 0;
+};
 int topk_keys_rows(const uint64_t *keys_in, int64_t n_rows, int64_t n, int64_t row_stride, int64_t piece_len,
                    int64_t piece_stride, int32_t k, uint64_t *keys_out, void *ws, size_t ws_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, const TopkOpts &opts = TopkOpts());
 int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k,
-                     int64_t doc_id_base, uint64_t *keys_out, void *ws, size_t ws_bytes, cudaStream_t st);
-size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k);
+                     int64_t doc_id_base, uint64_t *keys_out, void *ws, size_t ws_bytes, cudaStream_t st,
+                     const TopkOpts &opts = TopkOpts());
+size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k);       // for topk_scores_rows
+size_t topk_keys_ws_bytes(int64_t n_rows, int64_t n, int32_t k);  // for topk_keys_rows
 int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
                 int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st);
 

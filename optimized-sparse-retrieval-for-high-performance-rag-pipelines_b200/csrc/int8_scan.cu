@@ -136,7 +136,7 @@ extern "C" int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim,
     int64_t chunk = i8_chunk_docs(n_q, n_docs);
     int64_t n_chunks = (n_docs + chunk - 1) / chunk;
     *bytes = align_up((size_t)nq * chunk * 4, 256) + topk_ws_bytes(nq, chunk, k) +
-             align_up((size_t)n_chunks * nq * k * 8, 256) + topk_ws_bytes(nq, n_chunks * k, k) +
+             align_up((size_t)n_chunks * nq * k * 8, 256) + topk_keys_ws_bytes(nq, n_chunks * k, k) +
              align_up((size_t)nq * k * 8, 256) + 1024;
     return B2R_OK;
 }
@@ -170,7 +170,7 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
     size_t tk_ws = topk_ws_bytes(n_q, chunk, k);
     void *tk = carve(tk_ws);
     uint64_t *part = static_cast<uint64_t *>(carve((size_t)n_chunks * n_q * k * 8));
-    size_t mg_ws = topk_ws_bytes(n_q, n_chunks * k, k);
+    size_t mg_ws = topk_keys_ws_bytes(n_q, n_chunks * k, k);
     void *mg = carve(mg_ws);
     uint64_t *keys = keys_out ? keys_out : static_cast<uint64_t *>(carve((size_t)n_q * k * 8));
     for (int64_t c = 0; c < n_chunks; ++c) {

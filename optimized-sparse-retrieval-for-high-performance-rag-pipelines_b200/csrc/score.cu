@@ -8,6 +8,15 @@
 // a document occurs at most once in a term's posting list.  The grid is (queries, tiles) with the
 // query index fastest, so CTAs resident at the same time work on the same doc tile and share its
 // posting blocks through L2; HBM sees each posting once per batch.
+//
+// Two epilogues.  DENSE writes the f32 score vector (the reference's return value).  FUSED is the
+// search path: nothing is written but the few documents that beat a per-query threshold, appended to
+// a small candidate list.  The threshold is the exact k-th best key of a strided sample of doc tiles
+// (every 32nd / 16th tile, scored with the DENSE epilogue into a compact buffer and selected exactly), so
+// it is a valid lower bound of the final k-th best and the final top-k is the top-k of
+// (sample winners + candidates).  A query whose candidate list overflows is rescored exhaustively
+// by the gated DENSE + top-k kernels that follow (they exit at once for every other query), so the
+// result is exact for any corpus order; the gate is evaluated on the device, nothing synchronises.
 #include "common.cuh"
 
 namespace b2r {
@@ -55,29 +64,54 @@ __device__ __forceinline__ double load_val(const void *post_val, uint32_t p) {
 // only synchronisation is __syncwarp: no CTA barrier, no atomics, no load imbalance between warps
 // (a dense term's postings are split by sub-tile through dense_ptr; a sparse term's small block is
 // scanned by every warp, each keeping the postings that fall in its range).
-template <int KIND>
-__global__ void __launch_bounds__(SC_THREADS)
+enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1 };
+enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1, SC_TILES_REST = 2 };
+
+struct ScoreOut {
+    // DENSE
+    float *scores;          // [queries, scores_stride]; column = out_tile * tile_docs + doc in tile
+    int64_t scores_stride;
+    const int32_t *gate;    // optional: run only for queries with gate[q_local] > gate_cap
+    int32_t gate_cap;
+    // FUSED
+    const uint64_t *thr_keys;  // [queries, k]: sample winners, ranked; threshold = thr_keys[q*k + k-1]
+    int32_t k;
+    uint64_t *cand;         // [queries, cap]
+    int32_t *cand_cnt;      // [queries]
+    int32_t cap;
+    uint32_t n_docs;        // documents in this shard (tail of the last tile is padding)
+    uint32_t doc_id_base;
+};
+
+template <int KIND, int OUT>
+__global__ void __launch_bounds__(SC_THREADS, 6)  // 6 CTAs/SM is what 32 KB of accumulators per CTA allows
 score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
                    const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
                    const uint32_t *__restrict__ dense_ptr, int n_tiles, int tile_docs,
                    const int32_t *__restrict__ q_ptr, const int32_t *__restrict__ q_terms,
-                   const float *__restrict__ q_weights, const float *__restrict__ idf, int q0,
-                   float *__restrict__ scores, int64_t scores_stride) {
+                   const float *__restrict__ q_weights, const float *__restrict__ idf, int q0, int tile_mode,
+                   int tile_step, int n_y, ScoreOut o) {
     extern __shared__ double acc[];  // [tile_docs]
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = q0 + blockIdx.x;
-    const int tile = blockIdx.y;
+    const int ql = blockIdx.x;  // query index inside this launch's chunk
+    const int q = q0 + ql;
+    if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap) return;
     const int sub = tile_docs / B2R_SUBTILES;
-    const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
     double *acc_w = acc + w * sub;
     const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
+    const int qs = q_ptr[q], qe = q_ptr[q + 1];
+    // normally gridDim.y == n_y (one tile per CTA); the gated fallback launches few CTAs that walk the tiles
+  for (int y = blockIdx.y; y < n_y; y += gridDim.y) {
+    const int tile = tile_mode == SC_TILES_ALL ? y
+                     : tile_mode == SC_TILES_SAMPLE ? y * tile_step
+                                                    : y + y / (tile_step - 1) + 1;  // tiles with tile % step != 0
+    const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
     const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
 
     for (int i = lane * 2; i < sub; i += 64) *reinterpret_cast<double2 *>(acc_w + i) = make_double2(0.0, 0.0);
     __syncwarp();
 
-    const int qs = q_ptr[q], qe = q_ptr[q + 1];
     for (int j0 = qs; j0 < qe; j0 += 32) {
         const int nt = min(32, qe - j0);
         // lane j stages term j0+j: posting range of this warp (dense) or of the whole tile block (sparse)
@@ -136,30 +170,74 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         }
     }
 
-    float *out = scores + (int64_t)blockIdx.x * scores_stride + my_doc0;
-    for (int i = lane * 2; i < sub; i += 64) {
-        double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
-        *reinterpret_cast<float2 *>(out + i) = make_float2(__double2float_rn(a.x), __double2float_rn(a.y));
+    if (OUT == SC_OUT_DENSE) {
+        float *out = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * tile_docs + w * sub;
+        for (int i = lane * 2; i < sub; i += 64) {
+            double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            *reinterpret_cast<float2 *>(out + i) = make_float2(__double2float_rn(a.x), __double2float_rn(a.y));
+        }
+    } else {
+        const uint64_t thr = o.thr_keys[(int64_t)ql * o.k + o.k - 1];
+        const uint32_t thr_hi = (uint32_t)(thr >> 32);
+        // a document can only beat thr if its score is >= the threshold score (thr_hi == 0: no threshold yet)
+        const float thr_f = thr_hi ? unord_f32(thr_hi) : __int_as_float(0xff800000);
+        for (int i = lane * 2; i < sub; i += 64) {
+            double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            float f[2] = {__double2float_rn(a.x), __double2float_rn(a.y)};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t doc = my_doc0 + i + c;
+                if ((f[c] >= thr_f || thr_hi == 0) && doc < o.n_docs) {
+                    const uint64_t key = make_key(ord_f32(f[c]), o.doc_id_base + doc);
+                    if (key > thr) {
+                        const int slot = atomicAdd(o.cand_cnt + ql, 1);
+                        if (slot < o.cap) o.cand[(int64_t)ql * o.cap + slot] = key;
+                    }
+                }
+            }
+        }
     }
+    __syncwarp();
+  }  // tile loop
 }
 
-static int launch_score(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
-                        const float *idf, int q0, int nq, float *scores, int64_t stride, cudaStream_t st) {
-    if (nq == 0) return B2R_OK;
+// cand[q][0..k) = sample winners, cand_cnt[q] = k (the rest of cand was zeroed by a memset)
+__global__ void seed_candidates_kernel(const uint64_t *__restrict__ sample_keys, int nq, int k, int cap,
+                                       uint64_t *__restrict__ cand, int32_t *__restrict__ cand_cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * k) return;
+    int q = i / k, j = i - q * k;
+    cand[(int64_t)q * cap + j] = sample_keys[i];
+    if (j == 0) cand_cnt[q] = k;
+}
+
+struct ScoreLaunch {
+    const b2r_index *ix;
+    const int32_t *q_ptr, *q_terms;
+    const float *q_weights, *idf;
+    cudaStream_t st;
+};
+
+template <int OUT>
+static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
+    if (nq == 0 || n_y == 0) return B2R_OK;
+    const b2r_index *ix = L.ix;
     const size_t smem = (size_t)ix->tile_docs * sizeof(double);
-    dim3 grid((unsigned)nq, (unsigned)ix->n_tiles);
+    // a gated launch is expected to do nothing: keep its grid tiny (each CTA walks n_y / 4 tiles if it runs)
+    const int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : n_y;
+    dim3 grid((unsigned)nq, (unsigned)grid_y);
     if (ix->kind == B2R_KIND_BM25) {
-        B2R_CUDA(cudaFuncSetAttribute(score_tiles_kernel<B2R_KIND_BM25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        score_tiles_kernel<B2R_KIND_BM25><<<grid, SC_THREADS, smem, st>>>(
-            ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, q_ptr,
-            q_terms, q_weights, idf, q0, scores, stride);
+        auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;
+        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
+                                               ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms, L.q_weights, L.idf, q0,
+                                               tile_mode, tile_step, n_y, o);
     } else {
-        B2R_CUDA(cudaFuncSetAttribute(score_tiles_kernel<B2R_KIND_IMPACT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_tiles_kernel<B2R_KIND_IMPACT><<<grid, SC_THREADS, smem, st>>>(
-            ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, q_ptr,
-            q_terms, q_weights, idf, q0, scores, stride);
+        auto kern = score_tiles_kernel<B2R_KIND_IMPACT, OUT>;
+        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
+                                               ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms, L.q_weights, L.idf, q0,
+                                               tile_mode, tile_step, n_y, o);
     }
     B2R_LAUNCH_CHECK();
     return B2R_OK;
@@ -178,23 +256,97 @@ static int check_index(const b2r_index *ix) {
 
 static int64_t padded_docs(const b2r_index *ix) { return (int64_t)ix->n_tiles * ix->tile_docs; }
 
+// ---- fused-selection plan ------------------------------------------------------------------------
+constexpr int FUSED_MIN_TILES = 64;   // below this the plain score + select path is used
+constexpr int FUSED_MAX_K = 128;
+
+static bool g_fused_enabled = true;
+// optional CUDA-event bracket around the fused scoring launch (bench.py's roofline of the dominant kernel)
+static bool g_profile = false;
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+
+struct FusedPlan {
+    bool on;
+    int step;  // every step-th doc tile forms the threshold sample
+    int n_sample, n_rest, cap, shift;
+    int64_t sample_cols, sample_valid;
+};
+
+static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
+    FusedPlan p = {};
+    p.on = g_fused_enabled && !want_scores && k >= 1 && k <= FUSED_MAX_K && ix->n_tiles >= FUSED_MIN_TILES;
+    if (!p.on) return p;
+    // expected candidates ~ k * (step - 1) (negative-binomial tail); the list also holds the k sample winners
+    p.step = k <= 16 ? 32 : 16;
+    p.cap = k <= 16 ? 1024 : 4096;
+    p.n_sample = (ix->n_tiles + p.step - 1) / p.step;
+    p.n_rest = ix->n_tiles - p.n_sample;
+    p.shift = 0;
+    while ((1 << p.shift) < ix->tile_docs) ++p.shift;
+    p.sample_cols = (int64_t)p.n_sample * ix->tile_docs;
+    const int64_t last_tile = (int64_t)(p.n_sample - 1) * p.step;
+    int64_t last_valid = ix->n_docs - last_tile * ix->tile_docs;
+    if (last_valid > ix->tile_docs) last_valid = ix->tile_docs;
+    p.sample_valid = (int64_t)(p.n_sample - 1) * ix->tile_docs + last_valid;
+    if (p.sample_valid < k) p.on = false;
+    return p;
+}
+
+// workspace bytes needed to run `qc` queries in one pass
+static size_t pass_bytes(const b2r_index *ix, const FusedPlan &fp, int64_t qc, int k) {
+    const size_t full = align_up((size_t)padded_docs(ix) * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k);
+    if (!fp.on) return full;
+    return full + align_up((size_t)fp.sample_cols * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, fp.sample_valid, k) +
+           align_up((size_t)qc * k * 8, 256) + align_up((size_t)qc * fp.cap * 8, 256) + align_up((size_t)qc * 4, 256) +
+           topk_keys_ws_bytes(qc, fp.cap, k) + 256;
+}
+
 }  // namespace b2r
 
 using namespace b2r;
+
+// test / profiling hook: 0 disables the fused-selection path (plain score + select is used)
+extern "C" void b2r_set_fused_selection(int enabled) { b2r::g_fused_enabled = enabled != 0; }
+
+extern "C" int b2r_set_profiling(int enabled) {
+    if (enabled && !g_ev[0]) {
+        B2R_CUDA(cudaEventCreate(&g_ev[0]));
+        B2R_CUDA(cudaEventCreate(&g_ev[1]));
+    }
+    g_profile = enabled != 0;
+    return B2R_OK;
+}
+
+extern "C" int b2r_profile_fused_ms(float *ms, int32_t *n_tiles_scored) {
+    B2R_CHECK_ARG(ms && g_ev[0], "b2r_profile_fused_ms: profiling was never enabled");
+    B2R_CUDA(cudaEventSynchronize(g_ev[1]));
+    B2R_CUDA(cudaEventElapsedTime(ms, g_ev[0], g_ev[1]));
+    (void)n_tiles_scored;
+    return B2R_OK;
+}
+
+extern "C" int b2r_fused_plan(const b2r_index *ix, int32_t k, int32_t *n_sample_tiles, int32_t *tile_step,
+                              int32_t *cap) {
+    int rc = check_index(ix);
+    if (rc) return rc;
+    FusedPlan fp = fused_plan(ix, k, false);
+    if (n_sample_tiles) *n_sample_tiles = fp.on ? fp.n_sample : 0;
+    if (tile_step) *tile_step = fp.on ? fp.step : 0;
+    if (cap) *cap = fp.on ? fp.cap : 0;
+    return B2R_OK;
+}
 
 extern "C" int b2r_search_workspace(const b2r_index *ix, int32_t n_queries, int32_t k, size_t *min_bytes,
                                     size_t *full_bytes) {
     int rc = check_index(ix);
     if (rc) return rc;
     B2R_CHECK_ARG(n_queries >= 0 && k >= 0 && k <= B2R_TOPK_MAX_FAST, "b2r_search_workspace: bad n_queries/k");
-    const size_t row = (size_t)padded_docs(ix) * 4;
     const int kk = k > 0 ? k : 1;
-    const size_t keys = align_up((size_t)(n_queries > 0 ? n_queries : 1) * kk * 8, 256);
-    if (min_bytes) *min_bytes = align_up(row, 256) + topk_ws_bytes(1, ix->n_docs, kk) + keys + 512;
-    if (full_bytes) {
-        int64_t nq = n_queries > 0 ? n_queries : 1;
-        *full_bytes = align_up(row * (size_t)nq, 256) + topk_ws_bytes(nq, ix->n_docs, kk) + keys + 512;
-    }
+    const int64_t nq = n_queries > 0 ? n_queries : 1;
+    const FusedPlan fp = fused_plan(ix, kk, false);
+    const size_t keys = align_up((size_t)nq * kk * 8, 256);
+    if (min_bytes) *min_bytes = pass_bytes(ix, fp, 1, kk) + keys + 512;
+    if (full_bytes) *full_bytes = pass_bytes(ix, fp, nq, kk) + keys + 512;
     return B2R_OK;
 }
 
@@ -236,37 +388,103 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             return B2R_ERR_WORKSPACE;
         }
     }
+    ScoreLaunch L = {ix, q_ptr, q_terms, q_weights, idf, st};
 
     if (scores_out) {
-        rc = launch_score(ix, q_ptr, q_terms, q_weights, idf, 0, n_queries, scores_out, scores_stride, st);
+        ScoreOut o = {};
+        o.scores = scores_out;
+        o.scores_stride = scores_stride;
+        rc = launch_score<SC_OUT_DENSE>(L, 0, n_queries, SC_TILES_ALL, 1, ix->n_tiles, o);
         if (rc) return rc;
         if (k > 0) {
             rc = topk_scores_rows(scores_out, n_queries, ix->n_docs, scores_stride, k, ix->doc_id_base, keys, wp, left,
                                   st);
             if (rc) return rc;
         }
-    } else {
-        // score in query chunks sized by the workspace
-        const size_t row_bytes = (size_t)pad * 4;
-        int64_t qc = n_queries;
-        while (qc > 1 && align_up(row_bytes * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k) > left)
-            qc = (qc + 1) / 2;
-        if (align_up(row_bytes * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k) > left) {
-            set_error("b2r_search_batch: workspace too small (%zu bytes left, one query needs %zu)", left,
-                      align_up(row_bytes, 256) + topk_ws_bytes(1, ix->n_docs, k));
-            return B2R_ERR_WORKSPACE;
-        }
-        float *chunk = static_cast<float *>(carve(row_bytes * (size_t)qc));
-        for (int64_t q0 = 0; q0 < n_queries; q0 += qc) {
-            int nq = (int)((n_queries - q0) < qc ? (n_queries - q0) : qc);
-            rc = launch_score(ix, q_ptr, q_terms, q_weights, idf, (int)q0, nq, chunk, pad, st);
-            if (rc) return rc;
-            rc = topk_scores_rows(chunk, nq, ix->n_docs, pad, k, ix->doc_id_base, keys + q0 * k, wp, left, st);
-            if (rc) return rc;
-        }
+        if (k > 0) return decode_keys(keys, (int64_t)n_queries * k, idx_out, val_out, nullptr, 0, k, 0, st);
+        return B2R_OK;
     }
-    if (k > 0) return decode_keys(keys, (int64_t)n_queries * k, idx_out, val_out, nullptr, 0, k, 0, st);
-    return B2R_OK;
+
+    // queries are processed in chunks sized by the workspace
+    const FusedPlan fp = fused_plan(ix, k, false);
+    int64_t qc = n_queries;
+    while (qc > 1 && pass_bytes(ix, fp, qc, k) > left) qc = (qc + 1) / 2;
+    if (pass_bytes(ix, fp, qc, k) > left) {
+        set_error("b2r_search_batch: workspace too small (%zu bytes left, one query needs %zu)", left,
+                  pass_bytes(ix, fp, 1, k));
+        return B2R_ERR_WORKSPACE;
+    }
+    float *full = static_cast<float *>(carve((size_t)pad * 4 * (size_t)qc));
+    const size_t tk_full_bytes = topk_ws_bytes(qc, ix->n_docs, k);
+    void *tk_full = carve(tk_full_bytes);
+    float *samp = nullptr;
+    void *tk_samp = nullptr, *tk_cand = nullptr;
+    uint64_t *samp_keys = nullptr, *cand = nullptr;
+    int32_t *cand_cnt = nullptr;
+    size_t tk_samp_bytes = 0, tk_cand_bytes = 0;
+    if (fp.on) {
+        samp = static_cast<float *>(carve((size_t)fp.sample_cols * 4 * (size_t)qc));
+        tk_samp_bytes = topk_ws_bytes(qc, fp.sample_valid, k);
+        tk_samp = carve(tk_samp_bytes);
+        samp_keys = static_cast<uint64_t *>(carve((size_t)qc * k * 8));
+        cand = static_cast<uint64_t *>(carve((size_t)qc * fp.cap * 8));
+        cand_cnt = static_cast<int32_t *>(carve((size_t)qc * 4));
+        tk_cand_bytes = topk_keys_ws_bytes(qc, fp.cap, k);
+        tk_cand = carve(tk_cand_bytes);
+    }
+
+    for (int64_t q0 = 0; q0 < n_queries; q0 += qc) {
+        const int nq = (int)((n_queries - q0) < qc ? (n_queries - q0) : qc);
+        uint64_t *kout = keys + q0 * k;
+        TopkOpts gate;
+        if (fp.on) {
+            // 1. threshold sample: every step-th tile, exact top-k of the sample
+            ScoreOut so = {};
+            so.scores = samp;
+            so.scores_stride = fp.sample_cols;
+            rc = launch_score<SC_OUT_DENSE>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
+            if (rc) return rc;
+            TopkOpts map;
+            map.chunk_shift = fp.shift;
+            map.chunk_stride = (uint32_t)fp.step * (uint32_t)ix->tile_docs;
+            rc = topk_scores_rows(samp, nq, fp.sample_valid, fp.sample_cols, k, ix->doc_id_base, samp_keys, tk_samp,
+                                  tk_samp_bytes, st, map);
+            if (rc) return rc;
+            // 2. candidate lists seeded with the sample winners
+            B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)nq * fp.cap * 8, st));
+            seed_candidates_kernel<<<(nq * k + 255) / 256, 256, 0, st>>>(samp_keys, nq, k, fp.cap, cand, cand_cnt);
+            B2R_LAUNCH_CHECK();
+            // 3. all other tiles: score, keep only what beats the sample's k-th best
+            ScoreOut fo = {};
+            fo.thr_keys = samp_keys;
+            fo.k = k;
+            fo.cand = cand;
+            fo.cand_cnt = cand_cnt;
+            fo.cap = fp.cap;
+            fo.n_docs = (uint32_t)ix->n_docs;
+            fo.doc_id_base = (uint32_t)ix->doc_id_base;
+            if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[0], st));
+            rc = launch_score<SC_OUT_FUSED>(L, (int)q0, nq, SC_TILES_REST, fp.step, fp.n_rest, fo);
+            if (rc) return rc;
+            if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[1], st));
+            // 4. top-k of (sample winners + candidates)
+            rc = topk_keys_rows(cand, nq, fp.cap, fp.cap, fp.cap, 0, k, kout, tk_cand, tk_cand_bytes, st);
+            if (rc) return rc;
+            // 5. exact fallback, gated on the device to the queries whose list overflowed
+            gate.gate = cand_cnt;
+            gate.gate_cap = fp.cap;
+        }
+        ScoreOut o = {};
+        o.scores = full;
+        o.scores_stride = pad;
+        o.gate = gate.gate;
+        o.gate_cap = gate.gate_cap;
+        rc = launch_score<SC_OUT_DENSE>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, o);
+        if (rc) return rc;
+        rc = topk_scores_rows(full, nq, ix->n_docs, pad, k, ix->doc_id_base, kout, tk_full, tk_full_bytes, st, gate);
+        if (rc) return rc;
+    }
+    return decode_keys(keys, (int64_t)n_queries * k, idx_out, val_out, nullptr, 0, k, 0, st);
 }
 
 extern "C" size_t b2r_search_host_extra_bytes(int32_t n_queries, int64_t n_query_terms, int32_t k) {

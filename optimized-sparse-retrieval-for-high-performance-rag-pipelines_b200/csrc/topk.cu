@@ -39,12 +39,14 @@ template <bool KEYS_IN, int E>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict__ keys_in, int64_t n,
                    int64_t row_stride, int64_t piece_len, int64_t piece_stride, uint32_t id_base, int k,
-                   int64_t seg_len, uint64_t *__restrict__ out) {
+                   int64_t seg_len, uint64_t *__restrict__ out, int chunk_shift, uint32_t chunk_stride,
+                   const int32_t *__restrict__ gate, int gate_cap) {
     __shared__ uint64_t arr[TK_SN];
     __shared__ int cnt;
     constexpr int SUB = TK_THREADS * E;
     const int tid = threadIdx.x;
     const int64_t row = blockIdx.x;
+    if (gate != nullptr && gate[row] <= gate_cap) return;  // uniform: this row is not ours to compute
     const int seg = blockIdx.y, n_segs = gridDim.y;
     const int64_t seg_beg = (int64_t)seg * seg_len;
     const int64_t seg_end = min(n, seg_beg + seg_len);
@@ -110,7 +112,9 @@ topk_stream_kernel(const float *__restrict__ scores, const uint64_t *__restrict_
                 int64_t j = vec ? base + ((int64_t)(e >> 2) * TK_THREADS + tid) * 4 + (e & 3)
                                 : base + (int64_t)e * TK_THREADS + tid;
                 const bool c = (all || f[e] >= tau_f) && j < seg_end;
-                key[e] = c ? make_key(ord_f32(f[e]), id_base + (uint32_t)j) : 0ull;
+                uint32_t g = (uint32_t)j;
+                if (chunk_shift) g = (uint32_t)(j >> chunk_shift) * chunk_stride + (g & ((1u << chunk_shift) - 1u));
+                key[e] = c ? make_key(ord_f32(f[e]), id_base + g) : 0ull;
             }
         }
 
@@ -216,6 +220,8 @@ static size_t tk_keys_ws(int64_t n_rows, int64_t n, int32_t k) {
     }
 }
 
+size_t topk_keys_ws_bytes(int64_t n_rows, int64_t n, int32_t k) { return tk_keys_ws(n_rows, n, k) + 256; }
+
 size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k) {
     TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_SCORES);
     if (p.n_segs == 1) return 256;
@@ -225,7 +231,7 @@ size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k) {
 
 int topk_keys_rows(const uint64_t *keys_in, int64_t n_rows, int64_t n, int64_t row_stride, int64_t piece_len,
                    int64_t piece_stride, int32_t k, uint64_t *keys_out, void *ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, const TopkOpts &opts) {
     if (n_rows == 0) return B2R_OK;
     B2R_CHECK_ARG(k >= 1 && k <= B2R_TOPK_MAX_FAST, "top-k: k=%d outside [1,%d]", k, B2R_TOPK_MAX_FAST);
     char *wp = static_cast<char *>(ws);
@@ -245,7 +251,8 @@ int topk_keys_rows(const uint64_t *keys_in, int64_t n_rows, int64_t n, int64_t r
         }
         dim3 grid((unsigned)n_rows, (unsigned)p.n_segs);
         topk_stream_kernel<true, TK_E_KEYS><<<grid, TK_THREADS, 0, st>>>(nullptr, keys_in, n, row_stride, piece_len,
-                                                                         piece_stride, 0u, k, p.seg_len, dst);
+                                                                         piece_stride, 0u, k, p.seg_len, dst, 0, 0u,
+                                                                         opts.gate, opts.gate_cap);
         B2R_LAUNCH_CHECK();
         if (p.n_segs == 1) return B2R_OK;
         keys_in = dst;
@@ -257,7 +264,8 @@ int topk_keys_rows(const uint64_t *keys_in, int64_t n_rows, int64_t n, int64_t r
 }
 
 int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k,
-                     int64_t doc_id_base, uint64_t *keys_out, void *ws, size_t ws_bytes, cudaStream_t st) {
+                     int64_t doc_id_base, uint64_t *keys_out, void *ws, size_t ws_bytes, cudaStream_t st,
+                     const TopkOpts &opts) {
     if (n_rows == 0) return B2R_OK;
     B2R_CHECK_ARG(k >= 1 && k <= B2R_TOPK_MAX_FAST, "top-k: k=%d outside [1,%d]", k, B2R_TOPK_MAX_FAST);
     B2R_CHECK_ARG(doc_id_base >= 0 && doc_id_base + n < 0xFFFFFFFFll, "top-k: global doc index exceeds 2^32-2");
@@ -277,12 +285,16 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
         left -= need;
     }
     dim3 grid((unsigned)n_rows, (unsigned)p.n_segs);
-    topk_stream_kernel<false, TK_E_SCORES><<<grid, TK_THREADS, 0, st>>>(scores, nullptr, n, row_stride, n, 0,
-                                                                         (uint32_t)doc_id_base, k, p.seg_len, dst);
+    topk_stream_kernel<false, TK_E_SCORES><<<grid, TK_THREADS, 0, st>>>(
+        scores, nullptr, n, row_stride, n, 0, (uint32_t)doc_id_base, k, p.seg_len, dst, opts.chunk_shift,
+        opts.chunk_stride, opts.gate, opts.gate_cap);
     B2R_LAUNCH_CHECK();
     if (p.n_segs == 1) return B2R_OK;
     int64_t n2 = (int64_t)p.n_segs * k;
-    return topk_keys_rows(dst, n_rows, n2, n2, n2, 0, k, keys_out, wp, left, st);
+    TopkOpts o2;
+    o2.gate = opts.gate;
+    o2.gate_cap = opts.gate_cap;
+    return topk_keys_rows(dst, n_rows, n2, n2, n2, 0, k, keys_out, wp, left, st, o2);
 }
 
 // ------------------------------------------------------------------------------------------ decode

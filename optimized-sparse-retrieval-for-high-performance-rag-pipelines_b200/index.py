@@ -23,7 +23,14 @@ import torch
 
 from . import _abi
 
-__all__ = ["TermMajorIndex", "pack_queries", "queries_from_dense", "reference_idf", "reference_avgdl"]
+__all__ = ["TermMajorIndex", "pack_queries", "queries_from_dense", "reference_idf", "reference_avgdl",
+           "set_fused_selection"]
+
+
+def set_fused_selection(enabled: bool) -> None:
+    """Profiling / test hook: False makes search use the plain "score everything, then select" kernels
+    instead of the fused-selection pipeline (both are exact)."""
+    _abi.lib.b2r_set_fused_selection(1 if enabled else 0)
 
 
 def _cuda_device(device=None) -> torch.device:

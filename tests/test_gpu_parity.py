@@ -201,6 +201,33 @@ def test_bm25_search_vs_oracle_medium(b2r, tile_docs, k):
     assert np.array_equal(hi, wi) and np.array_equal(_bits(hv), _bits(val.cpu().numpy()))
 
 
+def test_fused_selection_equals_plain_path_and_survives_overflow(b2r):
+    """The fused path (threshold from every 16th tile + candidate lists) must equal the plain path; an
+    adversarial corpus whose sample tiles hold no matching document forces the candidate lists to overflow
+    and exercises the device-gated exhaustive fallback."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab, tile = 40_000 + 11, 3000, 256          # 157 tiles -> fused path is active
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 30, seed=21)
+    rows = np.repeat(np.arange(n_docs), np.diff(indptr))
+    keep = (rows // tile) % 16 != 0                          # empty every sample tile
+    data2, indices2 = data[keep], indices[keep]
+    indptr2 = np.zeros(n_docs + 1, np.int64); np.cumsum(np.bincount(rows[keep], minlength=n_docs), out=indptr2[1:])
+    q_ptr, q_terms, q_w = S.zipf_queries(48, n_vocab, seed=22)
+    for (d_, i_, p_) in ((data, indices, indptr), (data2, indices2, indptr2)):
+        idf = b2r.reference_idf(i_, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+        ix = b2r.TermMajorIndex.from_csr(d_, i_, p_, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=tile)
+        for k in (10, 100):
+            b2r.set_fused_selection(True)
+            fi, fv = ix.search(q_ptr, q_terms, q_w, k)
+            b2r.set_fused_selection(False)
+            pi, pv = ix.search(q_ptr, q_terms, q_w, k)
+            b2r.set_fused_selection(True)
+            assert torch.equal(fi, pi) and torch.equal(fv, pv), k
+            wi, wv = _oracle_topk((d_, i_, p_, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, k)
+            assert np.array_equal(fi.cpu().numpy(), wi), k
+            assert np.array_equal(_bits(fv.cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv))), k
+
+
 def test_bm25_edge_queries(b2r):
     from b200ret import synthetic as S
     n_docs, n_vocab = 3000, 500
