@@ -174,6 +174,8 @@ int b2r_decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *va
 /* INT8 dense similarity, out f32[n_q, n_docs] = f32((f64(dot) * f64(qscale[q])) * f64(dscale[d])). */
 int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,
                        const float *q_scale, const float *d_scale, float *out, void *stream);
+/* Test / profiling hook: 0 forces the dp4a kernel even for shapes the tcgen05 kernel supports. */
+void b2r_set_int8_mma(int enabled);
 /* Exhaustive INT8 scan with fused per-query top-k (never materialises [n_q, n_docs]). */
 int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim, int32_t k, size_t *bytes);
 int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,

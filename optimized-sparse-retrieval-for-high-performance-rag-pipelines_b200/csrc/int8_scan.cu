@@ -2,8 +2,13 @@
 // rag_system/core/retriever_registry.py:90-117, and the scan + argpartition of
 // QuantizedEmbeddingRetriever.search, :495-515).
 //
-// Round-1 kernel: shared-memory tiled dp4a (IDP.4A) contraction -- exact int32 dot products --
-// followed by the reference's f64 scale chain  f32((f64(dot) * f64(qs)) * f64(ds)).
+// The contraction is the one dense GEMM-shaped op of the hot path, so it runs on the 5th-generation
+// tensor cores: tcgen05.mma kind::i8 (M = 128 documents x N = 128 queries x K = 32 bytes per
+// instruction), operands in 128B-swizzled K-major shared-memory tiles, int32 accumulators in tensor
+// memory, read back with tcgen05.ld for the epilogue, which applies the reference's f64 scale chain
+// f32((f64(dot) * f64(qs)) * f64(ds)) -- exact int32 dots, so results are bit-identical.
+// Embedding widths that are not a multiple of 128 bytes (or exceed 768) take the shared-memory tiled
+// dp4a kernel below instead (same results).
 // b2r_int8_scan_topk walks the corpus in document chunks: dots of one chunk go to a workspace
 // tile [n_q, chunk], the streaming top-k (topk.cu) reduces it to k keys per query, and the
 // per-chunk winners are merged at the end, so [n_q, n_docs] is never materialised.
@@ -93,9 +98,188 @@ int8_dot_kernel(const int8_t *__restrict__ q8, int n_q, const int8_t *__restrict
     }
 }
 
+
+// =================================================================================================
+// tcgen05 (UMMA) INT8 path
+// =================================================================================================
+constexpr int MM_M = 128;        // documents per tile  = UMMA M = TMEM lanes
+constexpr int MM_N = 128;        // queries per tile    = UMMA N = TMEM columns (int32)
+constexpr int MM_KC = 128;       // bytes of K per shared-memory chunk = one 128B swizzle row
+constexpr int MM_UK = 32;        // bytes of K per tcgen05.mma kind::i8
+constexpr int MM_THREADS = 256;
+constexpr int MM_MAX_KC = 6;     // dim <= 768
+constexpr int MM_CHUNK_BYTES = MM_M * MM_KC;  // 16 KB: [128 rows][128 B], 8-row x 128 B swizzle atoms
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024 B)
+// | [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) @4, a/b format INT8 (1) @7/@10,
+// K-major A and B, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t umma_idesc_s8(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_s8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n"
+        :
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+
+// Copies rows [row0, row0+128) x bytes [0, dim) of a row-major int8 matrix into n_kc swizzled chunks:
+// byte (r, kc*128 + c*16 + b) -> chunk kc, offset r*128 + ((c ^ (r & 7)) << 4) + b  (zero fill past n_rows)
+__device__ __forceinline__ void mm_stage_tile(uint8_t *smem, const int8_t *__restrict__ g, int64_t row0, int64_t n_rows,
+                                              int dim, int n_kc) {
+    const int units_per_row = n_kc * 8;  // 16-byte units
+    for (int v = threadIdx.x; v < MM_M * units_per_row; v += MM_THREADS) {
+        const int r = v / units_per_row, u = v - r * units_per_row;
+        const int kc = u >> 3, c = u & 7;
+        int4 val = make_int4(0, 0, 0, 0);
+        if (row0 + r < n_rows) val = __ldg(reinterpret_cast<const int4 *>(g + (row0 + r) * (int64_t)dim) + u);
+        *reinterpret_cast<int4 *>(smem + kc * MM_CHUNK_BYTES + r * MM_KC + ((c ^ (r & 7)) << 4)) = val;
+    }
+}
+
+__global__ void __launch_bounds__(MM_THREADS, 1)
+int8_mma_kernel(const int8_t *__restrict__ q8, int n_q, const int8_t *__restrict__ d8, int64_t n_docs, int dim,
+                const float *__restrict__ q_scale, const float *__restrict__ d_scale, float *__restrict__ out,
+                int64_t out_stride) {
+    extern __shared__ uint8_t mm_smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(mm_smem_raw) + 1023) & ~uintptr_t(1023));
+    const int n_kc = dim / MM_KC;
+    uint8_t *sA = smem;                           // [n_kc][128][128]
+    uint8_t *sB = smem + n_kc * MM_CHUNK_BYTES;   // [n_kc][128][128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.y * MM_N;
+    const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)MM_N)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    mm_stage_tile(sB, q8, q0, n_q, dim, n_kc);    // the query tile stays resident
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = umma_idesc_s8(MM_M, MM_N);
+    uint32_t phase = 0;
+
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t doc0 = t * MM_M;
+        mm_stage_tile(sA, d8, doc0, n_docs, dim, n_kc);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async-proxy (MMA) reads
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                for (int kc = 0; kc < n_kc; ++kc) {
+#pragma unroll
+                    for (int ks = 0; ks < MM_KC / MM_UK; ++ks) {
+                        const uint64_t ad = umma_desc_sw128(smem_u32(sA + kc * MM_CHUNK_BYTES + ks * MM_UK));
+                        const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * MM_CHUNK_BYTES + ks * MM_UK));
+                        umma_s8(tmem_base, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                    }
+                }
+                // arrives on mbar when all MMAs above have completed (implies fence::before_thread_sync)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 smem_u32(&mbar))
+                             : "memory");
+            }
+            __syncwarp();
+        }
+        mbar_wait(smem_u32(&mbar), phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        if (warp < 4) {  // warp w reads TMEM lanes [32w, 32w+32): one document row per thread
+            const int64_t doc = doc0 + warp * 32 + lane;
+            const double ds = doc < n_docs ? (double)d_scale[doc] : 0.0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < MM_N; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int q = q0 + c0 + j;
+                    if (q < n_q && doc < n_docs) {
+                        const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], (double)__ldg(q_scale + q)), ds);
+                        out[(int64_t)q * out_stride + doc] = __double2float_rn(sc);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM accumulator and sA are free again
+    }
+
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MM_N)
+                     : "memory");
+    }
+}
+
+static bool mma_shape_ok(int dim, const void *q8, const void *d8) {
+    return dim % MM_KC == 0 && dim / MM_KC >= 1 && dim / MM_KC <= MM_MAX_KC &&
+           (reinterpret_cast<uintptr_t>(q8) & 15) == 0 && (reinterpret_cast<uintptr_t>(d8) & 15) == 0;
+}
+
+static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
+                           const float *ds, float *out, int64_t stride, cudaStream_t st) {
+    const int n_kc = dim / MM_KC;
+    const size_t smem = (size_t)2 * n_kc * MM_CHUNK_BYTES + 1024;
+    B2R_CUDA(cudaFuncSetAttribute(int8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M;
+    const int gy = (n_q + MM_N - 1) / MM_N;
+    int64_t gx = n_tiles < 148 ? n_tiles : 148;  // persistent: one CTA per SM walks the document tiles
+    B2R_CHECK_ARG(gy <= 65535, "int8 scan: too many query tiles");
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    int8_mma_kernel<<<grid, MM_THREADS, smem, st>>>(q8, n_q, d8, n_docs, dim, qs, ds, out, stride);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
+static bool g_int8_use_mma = true;
+
 static int launch_int8_dot(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
                            const float *ds, float *out, int64_t stride, cudaStream_t st) {
     if (n_q == 0 || n_docs == 0) return B2R_OK;
+    if (g_int8_use_mma && mma_shape_ok(dim, q8, d8)) return launch_int8_mma(q8, n_q, d8, n_docs, dim, qs, ds, out, stride, st);
     bool vec = (dim % 16 == 0) && ((reinterpret_cast<uintptr_t>(q8) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(d8) & 15) == 0);
     int64_t gx = (n_docs + I8_DT - 1) / I8_DT;
@@ -119,6 +303,9 @@ static int64_t i8_chunk_docs(int32_t n_q, int64_t n_docs) {
 }  // namespace b2r
 
 using namespace b2r;
+
+// test / profiling hook: 0 forces the dp4a kernel for every shape
+extern "C" void b2r_set_int8_mma(int enabled) { b2r::g_int8_use_mma = enabled != 0; }
 
 extern "C" int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,
                                   const float *q_scale, const float *d_scale, float *out, void *stream) {

@@ -27,7 +27,12 @@ import torch
 from . import _abi
 from .index import TermMajorIndex, _cuda_device, _stream_ptr, _to_device, queries_from_dense
 
-__all__ = ["simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
+def set_int8_mma(enabled: bool) -> None:
+    """Profiling / test hook: False forces the dp4a kernel for every shape (results are identical)."""
+    _abi.lib.b2r_set_int8_mma(1 if enabled else 0)
+
+
+__all__ = ["set_int8_mma", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
            "int8_scan_topk"]
 

@@ -122,6 +122,28 @@ def test_int8_odd_shapes(b2r):
         assert np.array_equal(_bits(got), _bits(np_oracle.int8_dot_batch(q8, d8, qs, ds))), (nq, n, dim)
 
 
+@pytest.mark.parametrize("nq,n,dim", [(300, 10_000, 768), (128, 4096, 128), (129, 1000, 512), (5, 130, 256)])
+def test_int8_tensor_core_path_equals_dp4a_and_oracle(b2r, nq, n, dim):
+    """tcgen05 kind::i8 kernel (dim % 128 == 0, dim <= 768) vs the dp4a kernel vs the oracle: bit-exact."""
+    rng = np.random.default_rng(nq + n + dim)
+    q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+    d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
+    qs = (rng.random(nq).astype(np.float32) + 0.01) / 127
+    ds = rng.random(n).astype(np.float32) + 0.01
+    b2r.set_int8_mma(True)
+    a = b2r.quantized_dot_product_batch(q8, d8, qs, ds)
+    b2r.set_int8_mma(False)
+    c = b2r.quantized_dot_product_batch(q8, d8, qs, ds)
+    b2r.set_int8_mma(True)
+    assert np.array_equal(_bits(a), _bits(c))
+    want = np_oracle.int8_dot_batch(q8, d8, qs, ds)
+    assert np.array_equal(_bits(a), _bits(want))
+    idx, val, _ = b2r.int8_scan_topk(q8, d8, qs, ds, 50)
+    for q in (0, nq // 2, nq - 1):
+        wi, wv = np_oracle.topk_canonical(want[q], 50)
+        assert np.array_equal(idx[q].cpu().numpy(), wi) and np.array_equal(_bits(val[q].cpu().numpy()), _bits(wv))
+
+
 # ----------------------------------------------------------------------------------- golden + edge: K2
 def test_topk_reference_cases(b2r, golden_dir):
     z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
