@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Measurements of the BASELINE.json configurations other than the headline one (they are parity-test
+cases, not bench lines): C3 (8.8M docs, top-100), C4 (SPLADE-shape impact dot), C5 (INT8 768-d scan).
+Synthetic corpora are generated on the GPU with torch (data generation only); every timed call goes
+through libb200ret.  Prints one JSON object per configuration.
+
+    python tools/bench_configs.py int8 [--docs N] [--queries Q ...]
+    python tools/bench_configs.py c3   [--docs N]
+    python tools/bench_configs.py c4   [--docs N]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import b200ret  # noqa: E402
+from b200ret import synthetic as S  # noqa: E402
+
+PEAK = 6540.8
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, steps=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def zipf_csr_torch(n_docs, n_vocab, mean_len, seed, dev, distinct_per_doc=None, chunk=1 << 20):
+    """GPU version of synthetic.zipf_corpus (different RNG stream, same law)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    p = 1.0 / torch.arange(1, n_vocab + 1, dtype=torch.float64, device=dev)
+    cdf = torch.cumsum(p / p.sum(), 0)
+    datas, inds, nnz_rows, lens_all = [], [], [], []
+    for lo in range(0, n_docs, chunk):
+        n = min(chunk, n_docs - lo)
+        if distinct_per_doc is None:
+            gam = torch.distributions.Gamma(torch.tensor(2.0, device=dev), torch.tensor(2.0 / mean_len, device=dev))
+            torch.manual_seed(seed + lo)
+            lens = torch.clamp(torch.floor(gam.sample((n,))), 5, 400).to(torch.int64)
+        else:
+            lens = torch.full((n,), distinct_per_doc * 3, dtype=torch.int64, device=dev)
+        tot = int(lens.sum())
+        toks = torch.clamp(torch.searchsorted(cdf, torch.rand(tot, device=dev, generator=g, dtype=torch.float64)),
+                           max=n_vocab - 1)
+        doc = torch.repeat_interleave(torch.arange(n, device=dev), lens)
+        key, _ = torch.sort(doc * n_vocab + toks)
+        del toks, doc
+        uniq, cnt = torch.unique_consecutive(key, return_counts=True)
+        del key
+        rows = uniq // n_vocab
+        if distinct_per_doc is not None:      # keep the first `distinct_per_doc` terms of every row
+            start = torch.searchsorted(rows, torch.arange(n, device=dev))
+            rank = torch.arange(len(uniq), device=dev) - start[rows]
+            keep = rank < distinct_per_doc
+            uniq, cnt, rows = uniq[keep], cnt[keep], rows[keep]
+        nnz_rows.append(torch.bincount(rows, minlength=n))
+        inds.append((uniq % n_vocab).to(torch.int32))
+        if distinct_per_doc is None:
+            datas.append(cnt.to(torch.float32))
+            lens_all.append(lens.to(torch.float32))
+        else:
+            gam = torch.distributions.Gamma(torch.tensor(2.0, device=dev), torch.tensor(2.0, device=dev))
+            datas.append(gam.sample((len(uniq),)).to(torch.float32))
+    indptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.cat(nnz_rows), 0, out=indptr[1:])
+    return torch.cat(datas), torch.cat(inds), indptr, (torch.cat(lens_all) if lens_all else None)
+
+
+def run_int8(args):
+    dev = torch.device("cuda")
+    n, dim, k = args.docs, 768, 100
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    d8 = torch.randint(-127, 128, (n, dim), device=dev, dtype=torch.int8, generator=g)
+    ds = torch.rand(n, device=dev, generator=g) + 0.01
+    out = []
+    for nq in args.queries:
+        q8 = torch.randint(-127, 128, (nq, dim), device=dev, dtype=torch.int8, generator=g)
+        qs = (torch.rand(nq, device=dev, generator=g) + 0.01) / 127
+        ms = timed(lambda: b200ret.int8_scan_topk(q8, d8, qs, ds, k), steps=3, warmup=1)
+        ops = 2.0 * nq * n * dim
+        rec = {"config": f"c5: INT8 {dim}-d exhaustive scan, {n} vectors, top-{k}", "queries": nq, "ms": ms,
+               "queries_per_s": nq / (ms * 1e-3), "int8_tops": ops / (ms * 1e-3) / 1e12,
+               "corpus_gbs": n * (dim + 4) / (ms * 1e-3) / 1e9}
+        if nq <= 64 and n <= 2_000_000:    # parity spot check on the first query against exact integer math
+            idx, val, _ = b200ret.int8_scan_topk(q8[:1], d8, qs[:1], ds, k)
+            dots = (d8.to(torch.int32) * q8[0].to(torch.int32)).sum(1).to(torch.float64)
+            sc = ((dots * qs[0].double()) * ds.double()).float()
+            top = torch.topk(sc, k, sorted=True)
+            rec["top_values_match"] = bool(torch.equal(top.values, val[0]))
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+    return out
+
+
+def run_sparse(args, kind):
+    dev = torch.device("cuda")
+    if kind == "c3":
+        n_docs, n_vocab, k, nq = args.docs, 100_000, 100, 1024
+        t0 = time.time()
+        data, ind, ptr, dl = zipf_csr_torch(n_docs, n_vocab, 60.0, 20260101, dev)
+        df = torch.bincount(ind, minlength=n_vocab).cpu().numpy()
+        idf = np.log((n_docs - df + 0.5) / (df + 0.5)).astype(np.float32)
+        avgdl = float(np.mean(dl.cpu().numpy()))
+        q_ptr, q_terms, q_w = S.zipf_queries(nq, n_vocab)
+        ix = b200ret.TermMajorIndex.from_csr(data, ind, ptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+        per = 12
+        desc = f"c3: synthetic Zipfian {n_docs} docs x 100K vocab, 1024 queries, BM25 top-{k}, 1 GPU"
+    else:
+        n_docs, n_vocab, k, nq = args.docs, 30522, 10, 256
+        t0 = time.time()
+        data, ind, ptr, _ = zipf_csr_torch(n_docs, n_vocab, 0, 20260103, dev, distinct_per_doc=120, chunk=1 << 18)
+        df = torch.bincount(ind, minlength=n_vocab).cpu().numpy()
+        idf = np.ones(n_vocab, np.float32)
+        q_ptr, q_terms, q_w = S.impact_queries(nq, n_vocab, 30)
+        ix = b200ret.TermMajorIndex.from_csr(data, ind, ptr, None, n_vocab=n_vocab, idf=idf, kind="impact")
+        per = 8
+        desc = f"c4: SPLADE-shape {n_docs} docs x 30522 vocab, ~120 nnz/doc, 30-term queries, impact dot top-{k}"
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    nnz = int(ptr[-1])
+    postings = int(df[q_terms].sum())
+    d_ptr, d_t, d_w = (torch.from_numpy(a).to(dev) for a in (q_ptr, q_terms, q_w))
+    ms = timed(lambda: ix.search(d_ptr, d_t, d_w, k), steps=5, warmup=2)
+    b200ret.set_fused_selection(False)
+    ms_plain = timed(lambda: ix.search(d_ptr, d_t, d_w, k), steps=3, warmup=1)
+    b200ret.set_fused_selection(True)
+    alg = per * postings + 8 * nq * n_docs
+    rec = {"config": desc, "nnz": nnz, "index_gb": ix.device_bytes() / 1e9, "gen_plus_build_s": build_s,
+           "postings_touched": postings, "ms_per_batch": ms, "queries_per_s": nq / (ms * 1e-3),
+           "ms_per_batch_plain_path": ms_plain, "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
+           "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / PEAK}
+    # parity spot check: first 3 queries against the oracle on the host copy of the CSR
+    if args.check:
+        from oracle import c_oracle
+        c = 3
+        h = [t.cpu().numpy() for t in (data, ind, ptr)]
+        idx, val = ix.search(q_ptr[:c + 1], q_terms[:q_ptr[c]], q_w[:q_ptr[c]], k)
+        ok = True
+        for q in range(c):
+            qtf = np.zeros(n_vocab, np.float32)
+            qtf[q_terms[q_ptr[q]:q_ptr[q + 1]]] = q_w[q_ptr[q]:q_ptr[q + 1]]
+            if kind == "c3":
+                s = c_oracle.bm25_scores(qtf, h[0], h[1], h[2], dl.cpu().numpy(), idf, 1.2, 0.75, avgdl)
+            else:
+                s = c_oracle.tfidf_scores(qtf, h[0], h[1], h[2], idf)
+            wi, wv = c_oracle.topk(s, k)
+            ok &= bool(np.array_equal(idx[q].cpu().numpy(), wi) and
+                       np.array_equal(val[q].cpu().numpy().view(np.uint32),
+                                      np.where(wv == 0, np.float32(0), wv).view(np.uint32)))
+        rec["bit_exact_vs_oracle_first_3_queries"] = ok
+    print(json.dumps(rec), flush=True)
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["int8", "c3", "c4"])
+    ap.add_argument("--docs", type=int, default=None)
+    ap.add_argument("--queries", type=int, nargs="+", default=[1, 64, 1024])
+    ap.add_argument("--check", type=int, default=1)
+    args = ap.parse_args()
+    if args.docs is None:
+        args.docs = {"int8": 2_000_000, "c3": 8_800_000, "c4": 2_200_000}[args.what]
+    if args.what == "int8":
+        run_int8(args)
+    else:
+        run_sparse(args, args.what)
+
+
+if __name__ == "__main__":
+    main()
