@@ -4,14 +4,17 @@
 //
 // The contraction is the one dense GEMM-shaped op of the hot path, so it runs on the 5th-generation
 // tensor cores: tcgen05.mma kind::i8 (M = 128 documents x N = 128 queries x K = 32 bytes per
-// instruction), operands in 128B-swizzled K-major shared-memory tiles, int32 accumulators in tensor
-// memory, read back with tcgen05.ld for the epilogue, which applies the reference's f64 scale chain
+// instruction), operands staged by TMA into 128B-swizzled K-major shared-memory tiles (the query tile
+// resident, document K-chunks through an mbarrier ring), int32 accumulators double-buffered in tensor
+// memory, read back with tcgen05.ld by the epilogue warps, which apply the reference's f64 scale chain
 // f32((f64(dot) * f64(qs)) * f64(ds)) -- exact int32 dots, so results are bit-identical.
 // Embedding widths that are not a multiple of 128 bytes (or exceed 768) take the shared-memory tiled
 // dp4a kernel below instead (same results).
 // b2r_int8_scan_topk walks the corpus in document chunks: dots of one chunk go to a workspace
 // tile [n_q, chunk], the streaming top-k (topk.cu) reduces it to k keys per query, and the
 // per-chunk winners are merged at the end, so [n_q, n_docs] is never materialised.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -106,7 +109,7 @@ constexpr int MM_M = 128;        // documents per tile  = UMMA M = TMEM lanes
 constexpr int MM_N = 128;        // queries per tile    = UMMA N = TMEM columns (int32)
 constexpr int MM_KC = 128;       // bytes of K per shared-memory chunk = one 128B swizzle row
 constexpr int MM_UK = 32;        // bytes of K per tcgen05.mma kind::i8
-constexpr int MM_THREADS = 256;
+constexpr int MM_THREADS = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 constexpr int MM_MAX_KC = 6;     // dim <= 768
 constexpr int MM_CHUNK_BYTES = MM_M * MM_KC;  // 16 KB: [128 rows][128 B], 8-row x 128 B swizzle atoms
 
@@ -142,87 +145,151 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-// Copies rows [row0, row0+128) x bytes [0, dim) of a row-major int8 matrix into n_kc swizzled chunks:
-// byte (r, kc*128 + c*16 + b) -> chunk kc, offset r*128 + ((c ^ (r & 7)) << 4) + b  (zero fill past n_rows)
-__device__ __forceinline__ void mm_stage_tile(uint8_t *smem, const int8_t *__restrict__ g, int64_t row0, int64_t n_rows,
-                                              int dim, int n_kc) {
-    const int units_per_row = n_kc * 8;  // 16-byte units
-    for (int v = threadIdx.x; v < MM_M * units_per_row; v += MM_THREADS) {
-        const int r = v / units_per_row, u = v - r * units_per_row;
-        const int kc = u >> 3, c = u & 7;
-        int4 val = make_int4(0, 0, 0, 0);
-        if (row0 + r < n_rows) val = __ldg(reinterpret_cast<const int4 *>(g + (row0 + r) * (int64_t)dim) + u);
-        *reinterpret_cast<int4 *>(smem + kc * MM_CHUNK_BYTES + r * MM_KC + ((c ^ (r & 7)) << 4)) = val;
-    }
+// ---- TMA + mbarrier helpers ---------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tiled bulk tensor copy global -> shared (128B-swizzled box), completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {  // arrive on bar when all prior MMAs have completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
 }
 
+constexpr int MM_MAX_STAGES = 8;
+struct MmBars {
+    uint64_t full[MM_MAX_STAGES];   // TMA landed a document K-chunk
+    uint64_t empty[MM_MAX_STAGES];  // the MMAs that read it have completed
+    uint64_t tfull[2];              // an accumulator (128 TMEM columns) is complete
+    uint64_t tempty[2];             // the epilogue has drained it
+    uint64_t bfull;                 // the resident query tile has landed
+};
+
+// Warp-specialised, persistent: CTA (x = query tile of 128, y) walks document tiles y, y+gridDim.y, ...
+//   warp 8 lane 0 : TMA producer  -- document tile K-chunks (128 docs x 128 B, SWIZZLE_128B) into a ring
+//   warp 9 lane 0 : MMA issuer    -- 4 x tcgen05.mma kind::i8 (M128 N128 K32) per chunk, accumulators in TMEM,
+//                                    double buffered (2 x 128 columns) so the epilogue overlaps the next tile
+//   warps 0-7     : epilogue      -- tcgen05.ld (one document row per thread; warp w reads TMEM lane quadrant
+//                                    w % 4 and column half w / 4), f64 scale chain, f32 stores
+// Query tiles are the fast grid dimension: CTAs that share a document tile run together and hit it in L2.
 __global__ void __launch_bounds__(MM_THREADS, 1)
-int8_mma_kernel(const int8_t *__restrict__ q8, int n_q, const int8_t *__restrict__ d8, int64_t n_docs, int dim,
-                const float *__restrict__ q_scale, const float *__restrict__ d_scale, float *__restrict__ out,
-                int64_t out_stride) {
+int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_q, int n_q,
+                int64_t n_docs, int n_kc, int n_stages, const float *__restrict__ q_scale,
+                const float *__restrict__ d_scale, float *__restrict__ out, int64_t out_stride) {
     extern __shared__ uint8_t mm_smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ MmBars bars;
     __shared__ uint32_t tmem_base_s;
+    __shared__ double qs_s[MM_N];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(mm_smem_raw) + 1023) & ~uintptr_t(1023));
-    const int n_kc = dim / MM_KC;
-    uint8_t *sA = smem;                           // [n_kc][128][128]
-    uint8_t *sB = smem + n_kc * MM_CHUNK_BYTES;   // [n_kc][128][128]
+    uint8_t *sB = smem;                          // [n_kc][128 queries][128 B]
+    uint8_t *sA = smem + n_kc * MM_CHUNK_BYTES;  // [n_stages][128 docs][128 B]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.y * MM_N;
+    const int q0 = blockIdx.x * MM_N;
     const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"((uint32_t)MM_N)
+                     "r"((uint32_t)(2 * MM_N))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    if (tid == 32) {
+        for (int i = 0; i < MM_MAX_STAGES; ++i) {
+            mbar_init(&bars.full[i], 1);
+            mbar_init(&bars.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.tfull[i], 1);
+            mbar_init(&bars.tempty[i], 8);  // one arrival per epilogue warp
+        }
+        mbar_init(&bars.bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    mm_stage_tile(sB, q8, q0, n_q, dim, n_kc);    // the query tile stays resident
+    if (tid < MM_N) qs_s[tid] = (q0 + tid < n_q) ? (double)q_scale[q0 + tid] : 0.0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t idesc = umma_idesc_s8(MM_M, MM_N);
-    uint32_t phase = 0;
 
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t doc0 = t * MM_M;
-        mm_stage_tile(sA, d8, doc0, n_docs, dim, n_kc);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async-proxy (MMA) reads
-        __syncthreads();
-        if (warp == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+    if (warp == 8) {
+        if (lane == 0) {  // ---- TMA producer
+            mbar_expect_tx(&bars.bfull, (uint32_t)(n_kc * MM_CHUNK_BYTES));
+            for (int kc = 0; kc < n_kc; ++kc) tma_load_2d(sB + kc * MM_CHUNK_BYTES, &map_q, kc * MM_KC, q0, &bars.bfull);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
                 for (int kc = 0; kc < n_kc; ++kc) {
-#pragma unroll
-                    for (int ks = 0; ks < MM_KC / MM_UK; ++ks) {
-                        const uint64_t ad = umma_desc_sw128(smem_u32(sA + kc * MM_CHUNK_BYTES + ks * MM_UK));
-                        const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * MM_CHUNK_BYTES + ks * MM_UK));
-                        umma_s8(tmem_base, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                    mbar_wait(smem_u32(&bars.empty[stage]), ph ^ 1);  // slot free (passes at once the first time round)
+                    mbar_expect_tx(&bars.full[stage], (uint32_t)MM_CHUNK_BYTES);
+                    tma_load_2d(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(t * MM_M), &bars.full[stage]);
+                    if (++stage == n_stages) {
+                        stage = 0;
+                        ph ^= 1;
                     }
                 }
-                // arrives on mbar when all MMAs above have completed (implies fence::before_thread_sync)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                 smem_u32(&mbar))
-                             : "memory");
             }
-            __syncwarp();
         }
-        mbar_wait(smem_u32(&mbar), phase);
-        phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        if (warp < 4) {  // warp w reads TMEM lanes [32w, 32w+32): one document row per thread
-            const int64_t doc = doc0 + warp * 32 + lane;
-            const double ds = doc < n_docs ? (double)d_scale[doc] : 0.0;
+        __syncwarp();
+    } else if (warp == 9) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t idesc = umma_idesc_s8(MM_M, MM_N);
+            mbar_wait(smem_u32(&bars.bfull), 0);
+            int stage = 0, acc = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
+                mbar_wait(smem_u32(&bars.tempty[acc]), acc_ph ^ 1);  // epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MM_N);
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(smem_u32(&bars.full[stage]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int ks = 0; ks < MM_KC / MM_UK; ++ks) {
+                        const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * MM_CHUNK_BYTES + ks * MM_UK));
+                        const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * MM_CHUNK_BYTES + ks * MM_UK));
+                        umma_s8(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                    }
+                    umma_commit(&bars.empty[stage]);  // frees the smem slot when these MMAs are done
+                    if (++stage == n_stages) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                }
+                umma_commit(&bars.tfull[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_ph ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {  // ---- epilogue warps 0..7: TMEM lane quadrant = warp % 4 (document rows), column half = warp / 4
+        const int quad = warp & 3, half = warp >> 2;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
+            const int64_t doc = t * MM_M + quad * 32 + lane;
+            const bool doc_ok = doc < n_docs;
+            const double ds = doc_ok ? (double)d_scale[doc] : 0.0;
+            mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c0 = 0; c0 < MM_N; c0 += 32) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = half * 64 + cc * 32;
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * MM_N + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -234,22 +301,42 @@ int8_mma_kernel(const int8_t *__restrict__ q8, int n_q, const int8_t *__restrict
                       "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == 1) {  // this warp's share of the accumulator is in registers: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.tempty[acc]);
+                }
+                float *optr = out + (int64_t)(q0 + c0) * out_stride + doc;
+                if (q0 + c0 + 32 <= n_q) {  // full column block (warp-uniform)
+                    if (doc_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int q = q0 + c0 + j;
-                    if (q < n_q && doc < n_docs) {
-                        const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], (double)__ldg(q_scale + q)), ds);
-                        out[(int64_t)q * out_stride + doc] = __double2float_rn(sc);
+                        for (int j = 0; j < 32; ++j) {
+                            const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
+                            optr[(int64_t)j * out_stride] = __double2float_rn(sc);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (q0 + c0 + j < n_q && doc_ok) {
+                            const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
+                            optr[(int64_t)j * out_stride] = __double2float_rn(sc);
+                        }
                     }
                 }
             }
+            if (++acc == 2) {
+                acc = 0;
+                acc_ph ^= 1;
+            }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // TMEM accumulator and sA are free again
     }
 
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MM_N)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * MM_N))
                      : "memory");
     }
 }
@@ -259,17 +346,57 @@ static bool mma_shape_ok(int dim, const void *q8, const void *d8) {
            (reinterpret_cast<uintptr_t>(q8) & 15) == 0 && (reinterpret_cast<uintptr_t>(d8) & 15) == 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_rowmajor_i8_map(CUtensorMap *map, const int8_t *base, int64_t n_rows, int dim) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        B2R_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) {
+            set_error("int8 scan: cuTensorMapEncodeTiled is not available from this driver");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n_rows};  // innermost first
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim};                   // bytes between rows
+    const cuuint32_t box[2] = {(cuuint32_t)MM_KC, (cuuint32_t)MM_M};   // 128 B x 128 rows, rows past the end read as 0
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("int8 scan: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return B2R_ERR_CUDA;
+    }
+    return B2R_OK;
+}
+
 static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
                            const float *ds, float *out, int64_t stride, cudaStream_t st) {
     const int n_kc = dim / MM_KC;
-    const size_t smem = (size_t)2 * n_kc * MM_CHUNK_BYTES + 1024;
+    int n_stages = (200 * 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
+    if (n_stages > MM_MAX_STAGES) n_stages = MM_MAX_STAGES;
+    const size_t smem = (size_t)(n_kc + n_stages) * MM_CHUNK_BYTES + 1024;
+    CUtensorMap map_d, map_q;
+    int rc = make_rowmajor_i8_map(&map_d, d8, n_docs, dim);
+    if (rc) return rc;
+    rc = make_rowmajor_i8_map(&map_q, q8, n_q, dim);
+    if (rc) return rc;
     B2R_CUDA(cudaFuncSetAttribute(int8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M;
-    const int gy = (n_q + MM_N - 1) / MM_N;
-    int64_t gx = n_tiles < 148 ? n_tiles : 148;  // persistent: one CTA per SM walks the document tiles
-    B2R_CHECK_ARG(gy <= 65535, "int8 scan: too many query tiles");
+    const int gx = (n_q + MM_N - 1) / MM_N;
+    // one CTA per SM in total; query tiles are the fast dimension so that a document tile is shared in L2
+    int64_t gy = 148 / gx;
+    if (gy < 1) gy = 1;
+    if (gy > n_tiles) gy = n_tiles;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    int8_mma_kernel<<<grid, MM_THREADS, smem, st>>>(q8, n_q, d8, n_docs, dim, qs, ds, out, stride);
+    int8_mma_kernel<<<grid, MM_THREADS, smem, st>>>(map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, out, stride);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
@@ -293,7 +420,7 @@ static int launch_int8_dot(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
 
 static int64_t i8_chunk_docs(int32_t n_q, int64_t n_docs) {
     // keep the per-chunk score tile around 1 GiB
-    int64_t c = ((int64_t)1 << 28) / (n_q > 0 ? n_q : 1);
+    int64_t c = ((int64_t)1 << 30) / (n_q > 0 ? n_q : 1);  // score tile of at most 4 GiB
     c = (c / 4096) * 4096;
     if (c < 4096) c = 4096;
     if (c > n_docs) c = (n_docs + 3) / 4 * 4;

@@ -18,7 +18,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "global_statistics", "gather_candidates", "ShardedBM25"]
+__all__ = ["shard_range", "global_statistics", "gather_candidates", "merge_shard_candidates", "sharded_int8_scan",
+           "ShardedBM25"]
 
 
 def shard_range(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
@@ -60,6 +61,33 @@ def gather_candidates(local_keys: torch.Tensor, group=None) -> torch.Tensor:
     else:   # gloo (CPU tests of the plumbing)
         dist.all_gather(list(out.unbind(0)), local_keys.contiguous(), group=group)
     return out
+
+
+def merge_shard_candidates(local_keys: torch.Tensor, k: int, group=None):
+    """all-gather the ranked [Q, k] candidate keys of every shard and merge them on the GPU
+    (b2r_merge_candidates).  Returns (idx i64[Q,k] global doc indices, val f32[Q,k])."""
+    from . import _abi
+    from .index import _stream_ptr
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    gathered = gather_candidates(local_keys, group)
+    nq = int(local_keys.shape[0])
+    dev = local_keys.device
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ws = torch.empty(nq * k * 8 + (1 << 20), dtype=torch.uint8, device=dev)
+    _abi.check(_abi.lib.b2r_merge_candidates(gathered.data_ptr(), world, nq, k, None, idx.data_ptr(), val.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "merge candidates")
+    return idx, val
+
+
+def sharded_int8_scan(queries_int8, local_corpus_int8, query_scales, local_corpus_scales, k: int, doc_id_base: int,
+                      group=None):
+    """Doc-sharded INT8 scan: this rank scans its slice (global ids = doc_id_base + local row), then the
+    k candidates per query cross NVLink and are merged."""
+    from .kernels import int8_scan_topk
+    _i, _v, keys = int8_scan_topk(queries_int8, local_corpus_int8, query_scales, local_corpus_scales, k,
+                                  doc_id_base=doc_id_base)
+    return merge_shard_candidates(keys, int(keys.shape[1]), group)
 
 
 class ShardedBM25:
