@@ -40,6 +40,21 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
 
 constexpr int SC_THREADS = 32 * B2R_SUBTILES;  // one warp per sub-tile of the CTA's doc tile
 
+// The accumulators are cleared by the copy engine (cp.async.bulk from this zero page), not by stores:
+// the LSU / shared-memory data pipe is the scorer's bottleneck and the bulk copy does not go through it.
+__device__ __align__(128) double g_zero_page[16384 / B2R_SUBTILES];  // one sub-tile of the largest tile
+
+__device__ __forceinline__ uint32_t sc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sc_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tSC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra SC_DONE;\n\tbra SC_WAIT;\n\tSC_DONE:\n\t}\n"
+        :
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+
 // acc[rel] += contribution of one posting (reference order of operations, no FMA contraction)
 template <int KIND>
 __device__ __forceinline__ void apply_posting(double *acc_w, uint32_t rel, double u_or_w, float w_idf, float w_q,
@@ -92,6 +107,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
                    const float *__restrict__ q_weights, const float *__restrict__ idf, int q0, int tile_mode,
                    int tile_step, int n_y, ScoreOut o) {
     extern __shared__ double acc[];  // [tile_docs]
+    __shared__ __align__(8) uint64_t zbar[B2R_SUBTILES];  // per warp: "my accumulators have been cleared"
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ql = blockIdx.x;  // query index inside this launch's chunk
@@ -100,17 +116,32 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     const int sub = tile_docs / B2R_SUBTILES;
     double *acc_w = acc + w * sub;
     const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
-    const int qs = q_ptr[q], qe = q_ptr[q + 1];
+    const uint32_t zbar_a = sc_smem_u32(&zbar[w]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(zbar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t zphase = 0;
     // normally gridDim.y == n_y (one tile per CTA); the gated fallback launches few CTAs that walk the tiles
   for (int y = blockIdx.y; y < n_y; y += gridDim.y) {
+    if (lane == 0) {  // clear my sub-tile's accumulators with one bulk copy; overlaps the term staging below
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar_a), "r"((uint32_t)(sub * 8))
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                sc_smem_u32(acc_w)),
+            "l"(g_zero_page), "r"((uint32_t)(sub * 8)), "r"(zbar_a)
+            : "memory");
+    }
+    const int qs = q_ptr[q], qe = q_ptr[q + 1];
     const int tile = tile_mode == SC_TILES_ALL ? y
                      : tile_mode == SC_TILES_SAMPLE ? y * tile_step
                                                     : y + y / (tile_step - 1) + 1;  // tiles with tile % step != 0
     const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
     const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
 
-    for (int i = lane * 2; i < sub; i += 64) *reinterpret_cast<double2 *>(acc_w + i) = make_double2(0.0, 0.0);
-    __syncwarp();
+    bool cleared = false;
 
     for (int j0 = qs; j0 < qe; j0 += 32) {
         const int nt = min(32, qe - j0);
@@ -133,6 +164,10 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
                 my_beg = blk_ptr[e];
                 my_end = blk_ptr[e + 1];
             }
+        }
+        if (!cleared) {  // the staging loads above were issued before this wait
+            sc_mbar_wait(zbar_a, zphase);
+            cleared = true;
         }
         for (int j = 0; j < nt; ++j) {
             const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
@@ -170,6 +205,8 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         }
     }
 
+    if (!cleared) sc_mbar_wait(zbar_a, zphase);  // query without terms
+    zphase ^= 1;
     if (OUT == SC_OUT_DENSE) {
         float *out = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * tile_docs + w * sub;
         for (int i = lane * 2; i < sub; i += 64) {
@@ -197,6 +234,8 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             }
         }
     }
+    // the next tile's bulk clear (async proxy) must not overtake this tile's accumulator reads (generic proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
   }  // tile loop
 }
