@@ -216,19 +216,50 @@ def run_b200(args):
         return float(ms.item())
 
     # ---- headline: inputs resident in HBM
-    step = lambda: sharded.search(d_ptr, d_terms, d_w, k)  # noqa: E731
+    eager_step = lambda: sharded.search(d_ptr, d_terms, d_w, k)  # noqa: E731
     for _ in range(args.warmup):
-        step()
+        eager_step()
     torch.cuda.synchronize()
+    step, graphed = eager_step, False
+    if args.cuda_graph:
+        # the step is a fixed sequence of ~12 launches (+ one NCCL all-gather): replay it as a CUDA graph so that
+        # launch latency does not bound the multi-GPU runs (the buffers of the captured step are reused)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eager_step()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    g_out = sharded.search(d_ptr, d_terms, d_w, k)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+
+            def step():
+                g.replay()
+                return g_out
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            graphed = True
+        except Exception as ex:      # capture is an optimisation, never a requirement
+            print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {ex}); timing eager launches",
+                  file=sys.stderr)
+            step = eager_step
+            torch.cuda.synchronize()
     n0 = lib.b2r_launch_count()
+    eager_step()
+    launches_per_step = int(lib.b2r_launch_count() - n0)
+    torch.cuda.synchronize()
     with ClockSampler(local) as clk:
         ms = timed(step, args.steps)
-    launches = int(lib.b2r_launch_count() - n0)
+    launches = launches_per_step * args.steps
     qps = nq * args.steps / (ms * 1e-3)
 
     # ---- parity gate on what was just timed: a few queries against the oracle (rank 0, whole corpus)
     idx, val = step()
     torch.cuda.synchronize()
+    idx, val = idx.clone(), val.clone()
     parity = None
     if rank == 0 and args.check > 0:
         from oracle import c_oracle
@@ -284,7 +315,7 @@ def run_b200(args):
     dense = None
     if fused:
         for _ in range(3 + args.steps):
-            step()
+            eager_step()
             t_ms = C.c_float(0)
             lib.b2r_profile_fused_ms(C.byref(t_ms), None)
             k_times.append(t_ms.value)
@@ -321,7 +352,7 @@ def run_b200(args):
                        "queries_per_step": nq, "sharding": f"doc-sharded x{world}", "tile_docs": args.tile_docs,
                        "l2": "inputs exceed L2: per step the index shard (%.2f GB) plus a %.2f GB score tile stream "
                              "through HBM; no flush needed" % (ix.device_bytes() / 1e9, nq * ix.padded_docs * 4 / 1e9),
-                       "postings_touched_per_step_rank0": postings,
+                       "postings_touched_per_step_rank0": postings, "cuda_graph_replay": graphed,
                        "selection": ("fused: threshold from every %dth tile, candidate cap %d" % (t_step.value, cap.value))
                        if fused else "plain: score vector + streaming select"},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
@@ -345,8 +376,12 @@ def run_b200(args):
                                    "sample": f"first {n_sample} of {nq} queries, full corpus, {dt:.1f} s of wall time"}
         emit(out)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Every collective of the run has completed on every rank by now.  Tearing the NCCL communicator down
+        # while a captured graph still references it was seen to hang, so leave without the teardown.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
@@ -375,6 +410,7 @@ def main():
     ap.add_argument("--tile-docs", type=int, default=4096)
     ap.add_argument("--check", type=int, default=4, help="queries checked against the oracle after timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="replay the timed step as a CUDA graph (0 = eager)")
     ap.add_argument("--n-queries", type=int, default=None, help="override the batch size (profiling only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -296,7 +296,7 @@ static int check_index(const b2r_index *ix) {
 static int64_t padded_docs(const b2r_index *ix) { return (int64_t)ix->n_tiles * ix->tile_docs; }
 
 // ---- fused-selection plan ------------------------------------------------------------------------
-constexpr int FUSED_MIN_TILES = 64;   // below this the plain score + select path is used
+constexpr int FUSED_MIN_TILES = 8;    // below this the plain score + select path is used
 constexpr int FUSED_MAX_K = 128;
 
 static bool g_fused_enabled = true;
