@@ -176,6 +176,9 @@ int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t 
                        const float *q_scale, const float *d_scale, float *out, void *stream);
 /* Test / profiling hook: 0 forces the dp4a kernel even for shapes the tcgen05 kernel supports. */
 void b2r_set_int8_mma(int enabled);
+/* Test / profiling hook: 0 = b2r_int8_scan_topk uses the plain chunked "dense tile + select" path;
+ * 1 = fused selection for batches of >= 512 queries (default); 2 = fused selection for every batch size. */
+void b2r_set_int8_fused(int enabled);
 /* Exhaustive INT8 scan with fused per-query top-k (never materialises [n_q, n_docs]). */
 int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim, int32_t k, size_t *bytes);
 int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,

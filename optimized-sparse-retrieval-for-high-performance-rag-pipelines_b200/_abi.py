@@ -75,6 +75,7 @@ SIGNATURES = {
     "b2r_decode_keys": (C.c_int, [_P, _I64, _P, _P, _P]),
     "b2r_int8_dot_batch": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _P, _P]),
     "b2r_set_int8_mma": (None, [C.c_int]),
+    "b2r_set_int8_fused": (None, [C.c_int]),
     "b2r_int8_scan_workspace": (C.c_int, [_I32, _I64, _I32, _I32, C.POINTER(_SZ)]),
     "b2r_int8_scan_topk": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
 }

@@ -184,20 +184,49 @@ struct MmBars {
 //   warps 0-7     : epilogue      -- tcgen05.ld (one document row per thread; warp w reads TMEM lane quadrant
 //                                    w % 4 and column half w / 4), f64 scale chain, f32 stores
 // Query tiles are the fast grid dimension: CTAs that share a document tile run together and hit it in L2.
+enum { MM_OUT_DENSE = 0, MM_OUT_FUSED = 1 };
+enum { MM_TILES_ALL = 0, MM_TILES_SAMPLE = 1, MM_TILES_REST = 2 };
+
+struct MmOut {
+    // DENSE: f32 scores, column = logical tile * 128 + row (logical == actual unless a sample is being scored)
+    float *out;
+    int64_t out_stride;
+    // optional gate (both epilogues): the CTA runs only if some query of its tile has gate[q] > gate_cap
+    const int32_t *gate;
+    int32_t gate_cap;
+    // FUSED: keep only documents whose key beats thr_keys[q*k + k-1]
+    const uint64_t *thr_keys;
+    int32_t k;
+    uint64_t *cand;      // [n_q, cap]
+    int32_t *cand_cnt;   // [n_q]
+    int32_t cap;
+    uint32_t doc_id_base;
+};
+
+template <int OUT>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_q, int n_q,
                 int64_t n_docs, int n_kc, int n_stages, const float *__restrict__ q_scale,
-                const float *__restrict__ d_scale, float *__restrict__ out, int64_t out_stride) {
+                const float *__restrict__ d_scale, int tile_mode, int tile_step, int64_t n_logical, MmOut o) {
     extern __shared__ uint8_t mm_smem_raw[];
     __shared__ MmBars bars;
     __shared__ uint32_t tmem_base_s;
     __shared__ double qs_s[MM_N];
+    __shared__ uint64_t thr_key_s[MM_N];
+    __shared__ float thr_f_s[MM_N];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(mm_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sB = smem;                          // [n_kc][128 queries][128 B]
     uint8_t *sA = smem + n_kc * MM_CHUNK_BYTES;  // [n_stages][128 docs][128 B]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * MM_N;
-    const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M;
+    const int64_t n_tiles = n_logical;  // logical tiles this launch covers; tile_of() maps them to document tiles
+    auto tile_of = [&](int64_t y) -> int64_t {
+        return tile_mode == MM_TILES_ALL ? y : tile_mode == MM_TILES_SAMPLE ? y * tile_step : y + y / (tile_step - 1) + 1;
+    };
+    if (o.gate != nullptr) {  // device-side gate of the exhaustive fallback (uniform per CTA)
+        const bool mine = tid < MM_N && q0 + tid < n_q && o.gate[q0 + tid] > o.gate_cap;
+        if (!__syncthreads_or(mine)) return;
+    }
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -217,7 +246,17 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
         mbar_init(&bars.bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < MM_N) qs_s[tid] = (q0 + tid < n_q) ? (double)q_scale[q0 + tid] : 0.0;
+    if (tid < MM_N) {
+        const bool qv = q0 + tid < n_q;
+        qs_s[tid] = qv ? (double)q_scale[q0 + tid] : 0.0;
+        if (OUT == MM_OUT_FUSED) {
+            const uint64_t thr = qv ? o.thr_keys[(int64_t)(q0 + tid) * o.k + o.k - 1] : ~0ull;
+            const uint32_t hi = (uint32_t)(thr >> 32);
+            thr_key_s[tid] = thr;
+            // a document can only beat thr if its score is >= the threshold score; no threshold -> -inf; no query -> +inf
+            thr_f_s[tid] = !qv ? __int_as_float(0x7f800000) : hi ? unord_f32(hi) : __int_as_float(0xff800000);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -233,7 +272,8 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(smem_u32(&bars.empty[stage]), ph ^ 1);  // slot free (passes at once the first time round)
                     mbar_expect_tx(&bars.full[stage], (uint32_t)MM_CHUNK_BYTES);
-                    tma_load_2d(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(t * MM_M), &bars.full[stage]);
+                    tma_load_2d(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(tile_of(t) * MM_M),
+                                &bars.full[stage]);
                     if (++stage == n_stages) {
                         stage = 0;
                         ph ^= 1;
@@ -280,7 +320,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
-            const int64_t doc = t * MM_M + quad * 32 + lane;
+            const int64_t doc = tile_of(t) * MM_M + quad * 32 + lane;
             const bool doc_ok = doc < n_docs;
             const double ds = doc_ok ? (double)d_scale[doc] : 0.0;
             mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
@@ -306,21 +346,37 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.tempty[acc]);
                 }
-                float *optr = out + (int64_t)(q0 + c0) * out_stride + doc;
-                if (q0 + c0 + 32 <= n_q) {  // full column block (warp-uniform)
-                    if (doc_ok) {
+                if (OUT == MM_OUT_DENSE) {
+                    float *optr = o.out + (int64_t)(q0 + c0) * o.out_stride + (t * MM_M + quad * 32 + lane);
+                    if (q0 + c0 + 32 <= n_q) {  // full column block (warp-uniform)
+                        if (doc_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
+                                optr[(int64_t)j * o.out_stride] = __double2float_rn(sc);
+                            }
+                        }
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
-                            optr[(int64_t)j * out_stride] = __double2float_rn(sc);
+                            if (q0 + c0 + j < n_q && doc_ok) {
+                                const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
+                                optr[(int64_t)j * o.out_stride] = __double2float_rn(sc);
+                            }
                         }
                     }
-                } else {
+                } else if (doc_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (q0 + c0 + j < n_q && doc_ok) {
-                            const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
-                            optr[(int64_t)j * out_stride] = __double2float_rn(sc);
+                        const float sc =
+                            __double2float_rn(__dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds));
+                        if (sc >= thr_f_s[c0 + j]) {  // rare
+                            const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
+                            if (key > thr_key_s[c0 + j]) {
+                                const int q = q0 + c0 + j;
+                                const int slot = atomicAdd(o.cand_cnt + q, 1);
+                                if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
+                            }
                         }
                     }
                 }
@@ -377,8 +433,11 @@ static int make_rowmajor_i8_map(CUtensorMap *map, const int8_t *base, int64_t n_
     return B2R_OK;
 }
 
+template <int OUT>
 static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
-                           const float *ds, float *out, int64_t stride, cudaStream_t st) {
+                           const float *ds, int tile_mode, int tile_step, int64_t n_logical, const MmOut &o,
+                           cudaStream_t st) {
+    if (n_q == 0 || n_logical == 0) return B2R_OK;
     const int n_kc = dim / MM_KC;
     int n_stages = (200 * 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
     if (n_stages > MM_MAX_STAGES) n_stages = MM_MAX_STAGES;
@@ -388,25 +447,35 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
     if (rc) return rc;
     rc = make_rowmajor_i8_map(&map_q, q8, n_q, dim);
     if (rc) return rc;
-    B2R_CUDA(cudaFuncSetAttribute(int8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M;
+    B2R_CUDA(cudaFuncSetAttribute(int8_mma_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int gx = (n_q + MM_N - 1) / MM_N;
     // one CTA per SM in total; query tiles are the fast dimension so that a document tile is shared in L2
     int64_t gy = 148 / gx;
     if (gy < 1) gy = 1;
-    if (gy > n_tiles) gy = n_tiles;
+    if (gy > n_logical) gy = n_logical;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    int8_mma_kernel<<<grid, MM_THREADS, smem, st>>>(map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, out, stride);
+    int8_mma_kernel<OUT><<<grid, MM_THREADS, smem, st>>>(map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, tile_mode,
+                                                         tile_step, n_logical, o);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
 
 static bool g_int8_use_mma = true;
 
+// dense scores of all documents; `gate` (optional) restricts the work to queries with gate[q] > gate_cap
 static int launch_int8_dot(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
-                           const float *ds, float *out, int64_t stride, cudaStream_t st) {
+                           const float *ds, float *out, int64_t stride, cudaStream_t st,
+                           const int32_t *gate = nullptr, int32_t gate_cap = 0) {
     if (n_q == 0 || n_docs == 0) return B2R_OK;
-    if (g_int8_use_mma && mma_shape_ok(dim, q8, d8)) return launch_int8_mma(q8, n_q, d8, n_docs, dim, qs, ds, out, stride, st);
+    if (g_int8_use_mma && mma_shape_ok(dim, q8, d8)) {
+        MmOut o = {};
+        o.out = out;
+        o.out_stride = stride;
+        o.gate = gate;
+        o.gate_cap = gate_cap;
+        return launch_int8_mma<MM_OUT_DENSE>(q8, n_q, d8, n_docs, dim, qs, ds, MM_TILES_ALL, 1,
+                                             (n_docs + MM_M - 1) / MM_M, o, st);
+    }
     bool vec = (dim % 16 == 0) && ((reinterpret_cast<uintptr_t>(q8) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(d8) & 15) == 0);
     int64_t gx = (n_docs + I8_DT - 1) / I8_DT;
@@ -442,16 +511,60 @@ extern "C" int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d
     return launch_int8_dot(q8, n_q, d8, n_docs, dim, q_scale, d_scale, out, n_docs, static_cast<cudaStream_t>(stream));
 }
 
+// fused selection for the scan (same scheme as the BM25 search path in score.cu): exact top-k of a strided
+// sample of 128-document tiles gives a per-query threshold, the rest of the corpus is scanned with an
+// epilogue that only appends documents beating it, overflowing queries fall back to the gated dense path
+struct I8Fused {
+    bool on;
+    int step, cap;
+    int64_t n_tiles, n_sample, n_rest, sample_cols, sample_valid;
+};
+static bool g_int8_fused = true;
+
+static int g_int8_fused_min_q = 512;  // below this the extra launches cost more than the score tile they save
+
+static I8Fused i8_fused_plan(int32_t n_q, int64_t n_docs, int dim, int k, bool shape_ok) {
+    I8Fused p = {};
+    p.n_tiles = (n_docs + MM_M - 1) / MM_M;
+    p.on = g_int8_fused && g_int8_use_mma && shape_ok && k <= 128 && p.n_tiles >= 256 && dim > 0 &&
+           n_q >= g_int8_fused_min_q;
+    if (!p.on) return p;
+    p.step = k <= 16 ? 32 : 16;
+    p.cap = k <= 16 ? 1024 : 4096;
+    p.n_sample = (p.n_tiles + p.step - 1) / p.step;
+    p.n_rest = p.n_tiles - p.n_sample;
+    p.sample_cols = p.n_sample * MM_M;
+    int64_t last_valid = n_docs - (p.n_sample - 1) * p.step * MM_M;
+    if (last_valid > MM_M) last_valid = MM_M;
+    p.sample_valid = (p.n_sample - 1) * MM_M + last_valid;
+    if (p.sample_valid < k) p.on = false;
+    return p;
+}
+
+static size_t i8_fused_bytes(const I8Fused &fp, int64_t nq, int k) {
+    if (!fp.on) return 0;
+    return align_up((size_t)nq * fp.sample_cols * 4, 256) + topk_ws_bytes(nq, fp.sample_valid, k) +
+           align_up((size_t)nq * k * 8, 256) + align_up((size_t)nq * fp.cap * 8, 256) + align_up((size_t)nq * 4, 256) +
+           topk_keys_ws_bytes(nq, fp.cap, k) + 256;
+}
+
+// enabled: 0 = plain chunked path; 1 = fused path for batches of >= 512 queries (default); 2 = fused path always
+extern "C" void b2r_set_int8_fused(int enabled) {
+    g_int8_fused = enabled != 0;
+    g_int8_fused_min_q = enabled >= 2 ? 1 : 512;
+}
+
 extern "C" int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim, int32_t k, size_t *bytes) {
-    (void)dim;
     B2R_CHECK_ARG(bytes && n_q >= 0 && n_docs >= 1 && k >= 1 && k <= B2R_TOPK_MAX_FAST,
                   "b2r_int8_scan_workspace: bad arguments");
     int64_t nq = n_q > 0 ? n_q : 1;
     int64_t chunk = i8_chunk_docs(n_q, n_docs);
     int64_t n_chunks = (n_docs + chunk - 1) / chunk;
+    const bool shape_ok = dim % MM_KC == 0 && dim / MM_KC >= 1 && dim / MM_KC <= MM_MAX_KC;
+    const I8Fused fp = i8_fused_plan(n_q, n_docs, dim, k, shape_ok);
     *bytes = align_up((size_t)nq * chunk * 4, 256) + topk_ws_bytes(nq, chunk, k) +
              align_up((size_t)n_chunks * nq * k * 8, 256) + topk_keys_ws_bytes(nq, n_chunks * k, k) +
-             align_up((size_t)nq * k * 8, 256) + 1024;
+             align_up((size_t)nq * k * 8, 256) + i8_fused_bytes(fp, nq, k) + 1024;
     return B2R_OK;
 }
 
@@ -487,17 +600,64 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
     size_t mg_ws = topk_keys_ws_bytes(n_q, n_chunks * k, k);
     void *mg = carve(mg_ws);
     uint64_t *keys = keys_out ? keys_out : static_cast<uint64_t *>(carve((size_t)n_q * k * 8));
+
+    TopkOpts gate;  // empty unless the fused path ran: then only overflowed queries take the dense path below
+    const I8Fused fp = i8_fused_plan(n_q, n_docs, dim, k, mma_shape_ok(dim, q8, d8));
+    if (fp.on) {
+        float *samp = static_cast<float *>(carve((size_t)n_q * fp.sample_cols * 4));
+        const size_t tks_bytes = topk_ws_bytes(n_q, fp.sample_valid, k);
+        void *tks = carve(tks_bytes);
+        uint64_t *samp_keys = static_cast<uint64_t *>(carve((size_t)n_q * k * 8));
+        uint64_t *cand = static_cast<uint64_t *>(carve((size_t)n_q * fp.cap * 8));
+        int32_t *cand_cnt = static_cast<int32_t *>(carve((size_t)n_q * 4));
+        const size_t tkc_bytes = topk_keys_ws_bytes(n_q, fp.cap, k);
+        void *tkc = carve(tkc_bytes);
+        // 1. exact top-k of every step-th 128-document tile
+        MmOut so = {};
+        so.out = samp;
+        so.out_stride = fp.sample_cols;
+        int rc = launch_int8_mma<MM_OUT_DENSE>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_SAMPLE, fp.step,
+                                               fp.n_sample, so, st);
+        if (rc) return rc;
+        TopkOpts map;
+        map.chunk_shift = 7;  // 128-document tiles
+        map.chunk_stride = (uint32_t)fp.step * (uint32_t)MM_M;
+        rc = topk_scores_rows(samp, n_q, fp.sample_valid, fp.sample_cols, k, doc_id_base, samp_keys, tks, tks_bytes, st,
+                              map);
+        if (rc) return rc;
+        // 2. candidate lists seeded with the sample winners; 3. scan the rest, keep what beats the threshold
+        B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)n_q * fp.cap * 8, st));
+        rc = seed_candidates(samp_keys, n_q, k, fp.cap, cand, cand_cnt, st);
+        if (rc) return rc;
+        MmOut fo = {};
+        fo.thr_keys = samp_keys;
+        fo.k = k;
+        fo.cand = cand;
+        fo.cand_cnt = cand_cnt;
+        fo.cap = fp.cap;
+        fo.doc_id_base = (uint32_t)doc_id_base;
+        rc = launch_int8_mma<MM_OUT_FUSED>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_REST, fp.step,
+                                           fp.n_rest, fo, st);
+        if (rc) return rc;
+        // 4. top-k of (sample winners + candidates)
+        rc = topk_keys_rows(cand, n_q, fp.cap, fp.cap, fp.cap, 0, k, keys, tkc, tkc_bytes, st);
+        if (rc) return rc;
+        gate.gate = cand_cnt;
+        gate.gate_cap = fp.cap;
+    }
+    // exhaustive chunked path: the whole job without the fused path, otherwise gated to overflowed queries
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int64_t d0 = c * chunk;
         const int64_t nd = (n_docs - d0) < chunk ? (n_docs - d0) : chunk;
-        int rc = launch_int8_dot(q8, n_q, d8 + d0 * dim, nd, dim, q_scale, d_scale + d0, tile, chunk, st);
+        int rc = launch_int8_dot(q8, n_q, d8 + d0 * dim, nd, dim, q_scale, d_scale + d0, tile, chunk, st, gate.gate,
+                                 gate.gate_cap);
         if (rc) return rc;
         rc = topk_scores_rows(tile, n_q, nd, chunk, k, doc_id_base + d0,
-                              n_chunks == 1 ? keys : part + c * (int64_t)n_q * k, tk, tk_ws, st);
+                              n_chunks == 1 ? keys : part + c * (int64_t)n_q * k, tk, tk_ws, st, gate);
         if (rc) return rc;
     }
     if (n_chunks > 1) {
-        int rc = topk_keys_rows(part, n_q, n_chunks * k, k, k, (int64_t)n_q * k, k, keys, mg, mg_ws, st);
+        int rc = topk_keys_rows(part, n_q, n_chunks * k, k, k, (int64_t)n_q * k, k, keys, mg, mg_ws, st, gate);
         if (rc) return rc;
     }
     return decode_keys(keys, (int64_t)n_q * k, idx_out, val_out, nullptr, 0, k, 0, st);

@@ -250,6 +250,14 @@ __global__ void seed_candidates_kernel(const uint64_t *__restrict__ sample_keys,
     if (j == 0) cand_cnt[q] = k;
 }
 
+int seed_candidates(const uint64_t *sample_keys, int nq, int k, int cap, uint64_t *cand, int32_t *cand_cnt,
+                    cudaStream_t st) {
+    if (nq == 0) return B2R_OK;
+    seed_candidates_kernel<<<(nq * k + 255) / 256, 256, 0, st>>>(sample_keys, nq, k, cap, cand, cand_cnt);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
 struct ScoreLaunch {
     const b2r_index *ix;
     const int32_t *q_ptr, *q_terms;
@@ -491,8 +499,8 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             if (rc) return rc;
             // 2. candidate lists seeded with the sample winners
             B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)nq * fp.cap * 8, st));
-            seed_candidates_kernel<<<(nq * k + 255) / 256, 256, 0, st>>>(samp_keys, nq, k, fp.cap, cand, cand_cnt);
-            B2R_LAUNCH_CHECK();
+            rc = seed_candidates(samp_keys, nq, k, fp.cap, cand, cand_cnt, st);
+            if (rc) return rc;
             // 3. all other tiles: score, keep only what beats the sample's k-th best
             ScoreOut fo = {};
             fo.thr_keys = samp_keys;

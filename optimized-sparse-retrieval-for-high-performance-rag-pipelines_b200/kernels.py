@@ -32,7 +32,13 @@ def set_int8_mma(enabled: bool) -> None:
     _abi.lib.b2r_set_int8_mma(1 if enabled else 0)
 
 
-__all__ = ["set_int8_mma", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
+def set_int8_fused(mode) -> None:
+    """Profiling / test hook: 0/False = plain chunked dense-tile + select path, 1/True = fused selection for
+    batches of >= 512 queries (default), 2 = fused selection for every batch size."""
+    _abi.lib.b2r_set_int8_fused(int(mode))
+
+
+__all__ = ["set_int8_mma", "set_int8_fused", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
            "int8_scan_topk"]
 

@@ -144,6 +144,32 @@ def test_int8_tensor_core_path_equals_dp4a_and_oracle(b2r, nq, n, dim):
         assert np.array_equal(idx[q].cpu().numpy(), wi) and np.array_equal(_bits(val[q].cpu().numpy()), _bits(wv))
 
 
+@pytest.mark.parametrize("k", [10, 100])
+def test_int8_fused_scan_equals_plain_and_survives_overflow(b2r, k):
+    """Fused scan (threshold from every 32nd/16th 128-doc tile, candidate lists) vs the plain chunked path vs exact
+    integer math; zeroing the sample tiles makes the threshold useless and forces the gated exhaustive fallback."""
+    rng = np.random.default_rng(77 + k)
+    nq, n, dim = 130, 70_000 + 13, 768
+    q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+    d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
+    qs = (rng.random(nq).astype(np.float32) + 0.01) / 127
+    ds = rng.random(n).astype(np.float32) + 0.01
+    d8_adv = d8.copy()
+    d8_adv[((np.arange(n) // 128) % 16) == 0] = 0           # every sample tile scores exactly 0
+    for corpus in (d8, d8_adv):
+        b2r.set_int8_fused(2)            # fused path regardless of the batch size
+        fi, fv, _ = b2r.int8_scan_topk(q8, corpus, qs, ds, k, doc_id_base=1000)
+        b2r.set_int8_fused(0)
+        pi, pv, _ = b2r.int8_scan_topk(q8, corpus, qs, ds, k, doc_id_base=1000)
+        b2r.set_int8_fused(1)
+        assert torch.equal(fi, pi) and torch.equal(fv, pv)
+        for q in (0, 64, nq - 1):
+            want = np_oracle.int8_dot_batch(q8[q:q + 1], corpus, qs[q:q + 1], ds)[0]
+            wi, wv = np_oracle.topk_canonical(want, k)
+            assert np.array_equal(fi[q].cpu().numpy(), wi + 1000)
+            assert np.array_equal(_bits(fv[q].cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
+
+
 # ----------------------------------------------------------------------------------- golden + edge: K2
 def test_topk_reference_cases(b2r, golden_dir):
     z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
