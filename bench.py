@@ -183,6 +183,7 @@ def run_b200(args):
 
     w = make_workload(args.workload, args.n_queries)
     n_docs, k = w["n_docs"], w["k"]
+    b200ret.set_bank_schedule(bool(args.bank_schedule))
     lo, hi = shard_range(n_docs, world, rank)
     s, e = w["indptr"][lo], w["indptr"][hi]
     ix = b200ret.TermMajorIndex.from_csr(w["data"][s:e], w["indices"][s:e], w["indptr"][lo:hi + 1] - s, w["dl"][lo:hi],
@@ -412,6 +413,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the timed step as a CUDA graph (0 = eager)")
     ap.add_argument("--n-queries", type=int, default=None, help="override the batch size (profiling only)")
+    ap.add_argument("--bank-schedule", type=int, default=1,
+                    help="0 = build the index without the bank schedule of dense segments (A/B measurement only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

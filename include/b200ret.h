@@ -61,7 +61,9 @@ typedef enum b2r_kind {
 
 /* Term-major index over one shard of documents.  A plain descriptor: the buffers belong to the
  * caller.  Postings of term t that fall in document tile T (tile_docs consecutive local docs) are
- * post_doc/post_val[blk_ptr[t*n_tiles+T] .. blk_ptr[t*n_tiles+T+1]), ordered by doc index.
+ * post_doc/post_val[blk_ptr[t*n_tiles+T] .. blk_ptr[t*n_tiles+T+1]), ordered by doc index
+ * (non-dense terms) or, for dense terms, by sub-tile and inside a sub-tile segment round-robin over the 16
+ * shared-memory accumulator slots (doc mod 16), which keeps the scorer's f64 read-modify-write conflict-free.
  * Terms that average >= B2R_DENSE_MIN_PER_TILE postings per tile ("dense" terms) additionally get
  * a row of sub-tile offsets (B2R_SUBTILES sub-tiles of tile_docs/B2R_SUBTILES docs per tile):
  * postings of dense term t in sub-tile S are [dense_ptr[r*(n_tiles*8+1)+S], dense_ptr[...+S+1])
@@ -136,6 +138,8 @@ int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q
 /* Test / profiling hook: 0 makes b2r_search_batch use the plain "score everything, then select" path
  * instead of the fused-selection path (both are exact). */
 void b2r_set_fused_selection(int enabled);
+/* Test / profiling hook: 0 = later index builds keep dense segments doc-ascending (no bank schedule). */
+void b2r_set_bank_schedule(int enabled);
 
 /* Profiling hooks used by bench.py: bracket the fused scoring launch of b2r_search_batch with CUDA
  * events on its stream; b2r_profile_fused_ms returns the duration of the most recent one.
@@ -176,6 +180,9 @@ int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t 
                        const float *q_scale, const float *d_scale, float *out, void *stream);
 /* Test / profiling hook: 0 forces the dp4a kernel even for shapes the tcgen05 kernel supports. */
 void b2r_set_int8_mma(int enabled);
+/* Test / profiling hook: largest thread-block cluster (1, 2, 4 or 8 query-tile CTAs sharing every document
+ * chunk by TMA multicast) the tcgen05 kernel may use; 1 = no clusters. */
+void b2r_set_int8_cluster(int max_cluster);
 /* Test / profiling hook: 0 = b2r_int8_scan_topk uses the plain chunked "dense tile + select" path;
  * 1 = fused selection for batches of >= 512 queries (default); 2 = fused selection for every batch size. */
 void b2r_set_int8_fused(int enabled);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "b2r_search_workspace": (C.c_int, [_PIX, _I32, _I32, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "b2r_search_batch": (C.c_int, [_PIX, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "b2r_set_fused_selection": (None, [C.c_int]),
+    "b2r_set_bank_schedule": (None, [C.c_int]),
     "b2r_set_profiling": (C.c_int, [C.c_int]),
     "b2r_profile_fused_ms": (C.c_int, [C.POINTER(C.c_float), _P]),
     "b2r_fused_plan": (C.c_int, [_PIX, _I32, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "b2r_decode_keys": (C.c_int, [_P, _I64, _P, _P, _P]),
     "b2r_int8_dot_batch": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _P, _P]),
     "b2r_set_int8_mma": (None, [C.c_int]),
+    "b2r_set_int8_cluster": (None, [C.c_int]),
     "b2r_set_int8_fused": (None, [C.c_int]),
     "b2r_int8_scan_workspace": (C.c_int, [_I32, _I64, _I32, _I32, C.POINTER(_SZ)]),
     "b2r_int8_scan_topk": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),

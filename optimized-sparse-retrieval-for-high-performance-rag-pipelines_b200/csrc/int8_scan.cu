@@ -163,6 +163,38 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// same, delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void tma_load_2d_mcast(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+          "h"(cta_mask)
+        : "memory");
+}
+// arrive on the barrier at this offset in every CTA of cta_mask when all prior MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_mcast(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {  // arrive on bar when all prior MMAs have completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -183,7 +215,11 @@ struct MmBars {
 //                                    double buffered (2 x 128 columns) so the epilogue overlaps the next tile
 //   warps 0-7     : epilogue      -- tcgen05.ld (one document row per thread; warp w reads TMEM lane quadrant
 //                                    w % 4 and column half w / 4), f64 scale chain, f32 stores
-// Query tiles are the fast grid dimension: CTAs that share a document tile run together and hit it in L2.
+// Query tiles are the fast grid dimension and form a thread-block cluster (up to 8 CTAs): every document
+// K-chunk is fetched from L2 ONCE per cluster and TMA-multicast into the same ring slot of every CTA (the
+// CTAs take turns issuing), which divides the L2->SM operand traffic -- the limiter of a 128 x 128 tile --
+// by the cluster size.  A ring slot is reused only after the MMAs of ALL CTAs of the cluster have read it
+// (multicast tcgen05.commit onto every CTA's `empty` barrier, arrival count = cluster size).
 enum { MM_OUT_DENSE = 0, MM_OUT_FUSED = 1 };
 enum { MM_TILES_ALL = 0, MM_TILES_SAMPLE = 1, MM_TILES_REST = 2 };
 
@@ -213,7 +249,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
     __shared__ uint32_t tmem_base_s;
     __shared__ double qs_s[MM_N];
     __shared__ uint64_t thr_key_s[MM_N];
-    __shared__ float thr_f_s[MM_N];
+    __shared__ float2 flt_s[MM_N];  // FUSED pre-filter: {f32 query scale, lowered f32 threshold}
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(mm_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sB = smem;                          // [n_kc][128 queries][128 B]
     uint8_t *sA = smem + n_kc * MM_CHUNK_BYTES;  // [n_stages][128 docs][128 B]
@@ -223,8 +259,13 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
     auto tile_of = [&](int64_t y) -> int64_t {
         return tile_mode == MM_TILES_ALL ? y : tile_mode == MM_TILES_SAMPLE ? y * tile_step : y + y / (tile_step - 1) + 1;
     };
-    if (o.gate != nullptr) {  // device-side gate of the exhaustive fallback (uniform per CTA)
-        const bool mine = tid < MM_N && q0 + tid < n_q && o.gate[q0 + tid] > o.gate_cap;
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    if (o.gate != nullptr) {  // device-side gate of the exhaustive fallback: uniform over the whole cluster
+        const int cq0 = (int)(blockIdx.x - crank) * MM_N;
+        bool mine = false;
+        for (int i = tid; i < (int)csize * MM_N; i += MM_THREADS)
+            mine |= cq0 + i < n_q && o.gate[cq0 + i] > o.gate_cap;
         if (!__syncthreads_or(mine)) return;
     }
 
@@ -237,7 +278,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
     if (tid == 32) {
         for (int i = 0; i < MM_MAX_STAGES; ++i) {
             mbar_init(&bars.full[i], 1);
-            mbar_init(&bars.empty[i], 1);
+            mbar_init(&bars.empty[i], csize);  // one multicast commit from every CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.tfull[i], 1);
@@ -253,12 +294,23 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
             const uint64_t thr = qv ? o.thr_keys[(int64_t)(q0 + tid) * o.k + o.k - 1] : ~0ull;
             const uint32_t hi = (uint32_t)(thr >> 32);
             thr_key_s[tid] = thr;
-            // a document can only beat thr if its score is >= the threshold score; no threshold -> -inf; no query -> +inf
-            thr_f_s[tid] = !qv ? __int_as_float(0x7f800000) : hi ? unord_f32(hi) : __int_as_float(0xff800000);
+            // Pre-filter in f32 (the exact f64 chain costs two 64-bit conversions per output, which paces the
+            // whole kernel).  p = fl(fl(dot * qs) * ds) differs from the exact score s by < 2^-22 |s| as long as
+            // nothing under/overflows (guaranteed for |qs|, |ds| in [1e-15, 1e15]: |dot| < 2^24 is exact in f32),
+            // so  s >= thr  implies  p >= thr - 2^-20 |thr|.  Anything else (odd scales, no threshold yet,
+            // NaN) lowers the filter to -inf: every document then takes the exact path, which is always right.
+            const float qf = qv ? q_scale[q0 + tid] : 0.0f;
+            const float thr_f = hi ? unord_f32(hi) : __int_as_float(0xff800000);
+            const bool sane = fabsf(qf) >= 1e-15f && fabsf(qf) <= 1e15f && hi != 0 && fabsf(thr_f) <= 3e38f;
+            float lo_f = sane ? __fsub_rn(__fsub_rn(thr_f, __fmul_rn(fabsf(thr_f), 9.5367431640625e-07f)), 1e-37f)
+                              : __int_as_float(0xff800000);
+            if (!qv) lo_f = __int_as_float(0x7f800000);  // no query in this column: nothing passes
+            flt_s[tid] = make_float2(qf, lo_f);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrival
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
@@ -267,13 +319,20 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
             mbar_expect_tx(&bars.bfull, (uint32_t)(n_kc * MM_CHUNK_BYTES));
             for (int kc = 0; kc < n_kc; ++kc) tma_load_2d(sB + kc * MM_CHUNK_BYTES, &map_q, kc * MM_KC, q0, &bars.bfull);
             int stage = 0;
-            uint32_t ph = 0;
+            uint32_t ph = 0, turn = 0;
             for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
                 for (int kc = 0; kc < n_kc; ++kc) {
-                    mbar_wait(smem_u32(&bars.empty[stage]), ph ^ 1);  // slot free (passes at once the first time round)
+                    // slot free in EVERY CTA of the cluster (passes at once the first time round)
+                    mbar_wait(smem_u32(&bars.empty[stage]), ph ^ 1);
                     mbar_expect_tx(&bars.full[stage], (uint32_t)MM_CHUNK_BYTES);
-                    tma_load_2d(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(tile_of(t) * MM_M),
-                                &bars.full[stage]);
+                    if (csize == 1) {
+                        tma_load_2d(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(tile_of(t) * MM_M),
+                                    &bars.full[stage]);
+                    } else if (turn == crank) {  // my turn: one L2 read, delivered to all CTAs of the cluster
+                        tma_load_2d_mcast(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(tile_of(t) * MM_M),
+                                          &bars.full[stage], cmask);
+                    }
+                    if (++turn == csize) turn = 0;
                     if (++stage == n_stages) {
                         stage = 0;
                         ph ^= 1;
@@ -301,7 +360,9 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                         const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * MM_CHUNK_BYTES + ks * MM_UK));
                         umma_s8(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
                     }
-                    umma_commit(&bars.empty[stage]);  // frees the smem slot when these MMAs are done
+                    // frees the smem slot (in every CTA of the cluster) when these MMAs are done
+                    if (csize == 1) umma_commit(&bars.empty[stage]);
+                    else umma_commit_mcast(&bars.empty[stage], cmask);
                     if (++stage == n_stages) {
                         stage = 0;
                         ph ^= 1;
@@ -322,7 +383,9 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
         for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
             const int64_t doc = tile_of(t) * MM_M + quad * 32 + lane;
             const bool doc_ok = doc < n_docs;
-            const double ds = doc_ok ? (double)d_scale[doc] : 0.0;
+            const float dsf = doc_ok ? d_scale[doc] : 0.0f;
+            const double ds = (double)dsf;
+            const bool ds_sane = fabsf(dsf) >= 1e-15f && fabsf(dsf) <= 1e15f;
             mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -366,16 +429,32 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                         }
                     }
                 } else if (doc_ok) {
+                    // 1. f32 pre-filter over the 32 columns: one bit per column that may beat its threshold
+                    uint32_t hit = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float sc =
-                            __double2float_rn(__dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds));
-                        if (sc >= thr_f_s[c0 + j]) {  // rare
-                            const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
-                            if (key > thr_key_s[c0 + j]) {
-                                const int q = q0 + c0 + j;
-                                const int slot = atomicAdd(o.cand_cnt + q, 1);
-                                if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
+                        const float2 f = flt_s[c0 + j];
+                        const float p = __fmul_rn(__fmul_rn((float)(int32_t)v[j], f.x), dsf);
+                        hit |= (p < f.y) ? 0u : (1u << j);  // NaN passes
+                    }
+                    if (!ds_sane) hit = 0xffffffffu;
+                    // 2. exact f64 chain for the survivors only (8 columns at a time: most groups are empty)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if ((hit >> (8 * g)) & 0xffu) {
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const int j = 8 * g + jj;
+                                if ((hit >> j) & 1u) {
+                                    const float sc = __double2float_rn(
+                                        __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds));
+                                    const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
+                                    if (key > thr_key_s[c0 + j]) {
+                                        const int q = q0 + c0 + j;
+                                        const int slot = atomicAdd(o.cand_cnt + q, 1);
+                                        if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
+                                    }
+                                }
                             }
                         }
                     }
@@ -390,6 +469,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * MM_N))
@@ -433,6 +513,8 @@ static int make_rowmajor_i8_map(CUtensorMap *map, const int8_t *base, int64_t n_
     return B2R_OK;
 }
 
+static int g_int8_cluster = 4;  // largest cluster the launch may use (1 = no multicast)
+
 template <int OUT>
 static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
                            const float *ds, int tile_mode, int tile_step, int64_t n_logical, const MmOut &o,
@@ -448,14 +530,37 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
     rc = make_rowmajor_i8_map(&map_q, q8, n_q, dim);
     if (rc) return rc;
     B2R_CUDA(cudaFuncSetAttribute(int8_mma_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int gx = (n_q + MM_N - 1) / MM_N;
-    // one CTA per SM in total; query tiles are the fast dimension so that a document tile is shared in L2
-    int64_t gy = 148 / gx;
+    int gx = (n_q + MM_N - 1) / MM_N;
+    // query tiles form a cluster (power of two, at most g_int8_cluster CTAs) that shares every document K-chunk
+    // by multicast; gx is padded to a multiple of it (a padded CTA sees only out-of-range queries: zero
+    // operand, no output)
+    int csize = 1;
+    while (csize * 2 <= g_int8_cluster && csize < gx) csize <<= 1;
+    gx = (gx + csize - 1) / csize * csize;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(MM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // The kernel is persistent (a CTA walks document tiles with stride gridDim.y), so the grid must be ONE
+    // wave: at most as many clusters as the GPU can hold at once (a cluster lives inside one GPC, so this is
+    // fewer CTAs than SMs for large clusters) -- a second wave would double the run time.
+    cfg.gridDim = dim3((unsigned)gx, 1);
+    int max_clusters = 0;
+    B2R_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, int8_mma_kernel<OUT>, &cfg));
+    if (max_clusters < 1) max_clusters = 1;
+    int64_t gy = (int64_t)max_clusters / (gx / csize);
     if (gy < 1) gy = 1;
     if (gy > n_logical) gy = n_logical;
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    int8_mma_kernel<OUT><<<grid, MM_THREADS, smem, st>>>(map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, tile_mode,
-                                                         tile_step, n_logical, o);
+    cfg.gridDim = dim3((unsigned)gx, (unsigned)gy);
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, int8_mma_kernel<OUT>, map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, tile_mode,
+                                tile_step, n_logical, o));
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
@@ -500,8 +605,12 @@ static int64_t i8_chunk_docs(int32_t n_q, int64_t n_docs) {
 
 using namespace b2r;
 
-// test / profiling hook: 0 forces the dp4a kernel for every shape
+// test / profiling hooks: b2r_set_int8_mma(0) forces the dp4a kernel for every shape;
+// b2r_set_int8_cluster(c) caps the thread-block cluster (TMA multicast group) of the tcgen05 kernel at c CTAs
 extern "C" void b2r_set_int8_mma(int enabled) { b2r::g_int8_use_mma = enabled != 0; }
+extern "C" void b2r_set_int8_cluster(int max_cluster) {
+    b2r::g_int8_cluster = max_cluster < 1 ? 1 : max_cluster > 8 ? 8 : max_cluster;
+}
 
 extern "C" int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t n_docs, int32_t dim,
                                   const float *q_scale, const float *d_scale, float *out, void *stream) {

@@ -55,16 +55,20 @@ __device__ __forceinline__ void sc_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-// acc[rel] += contribution of one posting (reference order of operations, no FMA contraction)
-template <int KIND>
+// acc[rel] += contribution of one posting (reference order of operations, no FMA contraction).
+// FIRST: this is the first term that touches the warp's (freshly cleared) sub-tile, so the accumulator is
+// known to be +0.0 and is not read back: a store instead of a read-modify-write on the shared-memory pipe.
+// `0.0 + x` is still evaluated so that the stored bits are those of the reference's `acc += x`.
+template <int KIND, bool FIRST>
 __device__ __forceinline__ void apply_posting(double *acc_w, uint32_t rel, double u_or_w, float w_idf, float w_q,
                                               double w_idf64, double w_q64) {
+    const double a = FIRST ? 0.0 : acc_w[rel];
     if (KIND == B2R_KIND_BM25) {
-        acc_w[rel] = __dadd_rn(acc_w[rel], __dmul_rn(__dmul_rn(w_idf64, u_or_w), w_q64));
+        acc_w[rel] = __dadd_rn(a, __dmul_rn(__dmul_rn(w_idf64, u_or_w), w_q64));
     } else {
         // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens: see oracle/np_oracle.py
         float c = __fmul_rn(__fmul_rn((float)u_or_w, w_q), w_idf);
-        acc_w[rel] = __dadd_rn(acc_w[rel], (double)c);
+        acc_w[rel] = __dadd_rn(a, (double)c);
     }
 }
 
@@ -72,6 +76,41 @@ template <int KIND>
 __device__ __forceinline__ double load_val(const void *post_val, uint32_t p) {
     if (KIND == B2R_KIND_BM25) return ld_stream_f64(static_cast<const double *>(post_val) + p);
     return (double)ld_stream_f32(static_cast<const float *>(post_val) + p);
+}
+
+// One term applied by one warp to its own sub-tile.  dense: [beg, end) are exactly the warp's postings;
+// otherwise [beg, end) is the tile's (small) block and the warp keeps the postings of its doc range.
+template <int KIND, bool FIRST>
+__device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end, int lane, int sub, uint32_t my_doc0,
+                                           const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
+                                           double *acc_w, float w_idf, float w_q) {
+    const double w_idf64 = (double)w_idf, w_q64 = (double)w_q;
+    if (dense) {
+        uint32_t p = beg + lane;
+        for (; p + 96 < end; p += 128) {  // 4 independent postings in flight per lane
+            uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + 32);
+            uint32_t d2 = ld_stream_u32(post_doc + p + 64), d3 = ld_stream_u32(post_doc + p + 96);
+            double u0 = load_val<KIND>(post_val, p), u1 = load_val<KIND>(post_val, p + 32);
+            double u2 = load_val<KIND>(post_val, p + 64), u3 = load_val<KIND>(post_val, p + 96);
+            apply_posting<KIND, FIRST>(acc_w, d0 - my_doc0, u0, w_idf, w_q, w_idf64, w_q64);
+            apply_posting<KIND, FIRST>(acc_w, d1 - my_doc0, u1, w_idf, w_q, w_idf64, w_q64);
+            apply_posting<KIND, FIRST>(acc_w, d2 - my_doc0, u2, w_idf, w_q, w_idf64, w_q64);
+            apply_posting<KIND, FIRST>(acc_w, d3 - my_doc0, u3, w_idf, w_q, w_idf64, w_q64);
+        }
+        for (; p < end; p += 32) {
+            uint32_t d = ld_stream_u32(post_doc + p);
+            double u = load_val<KIND>(post_val, p);
+            apply_posting<KIND, FIRST>(acc_w, d - my_doc0, u, w_idf, w_q, w_idf64, w_q64);
+        }
+    } else {
+        for (uint32_t p = beg + lane; p < end; p += 32) {
+            const uint32_t rel = __ldg(post_doc + p) - my_doc0;  // blocks are shared by the 8 warps: keep in L1
+            if (rel < (uint32_t)sub) {
+                double u = load_val<KIND>(post_val, p);
+                apply_posting<KIND, FIRST>(acc_w, rel, u, w_idf, w_q, w_idf64, w_q64);
+            }
+        }
+    }
 }
 
 // One CTA = one (query, doc tile); one WARP = one sub-tile of tile_docs/8 docs whose f64 accumulators
@@ -142,6 +181,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
 
     bool cleared = false;
+    bool first = true;  // no term has touched this warp's sub-tile yet (warp-uniform)
 
     for (int j0 = qs; j0 < qe; j0 += 32) {
         const int nt = min(32, qe - j0);
@@ -174,33 +214,9 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             if (beg == end) continue;  // warp-uniform
             const int dense = __shfl_sync(full, my_dense, j);
             const float w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
-            const double w_idf64 = (double)w_idf, w_q64 = (double)w_q;
-            if (dense) {
-                uint32_t p = beg + lane;
-                for (; p + 96 < end; p += 128) {  // 4 independent postings in flight per lane
-                    uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + 32);
-                    uint32_t d2 = ld_stream_u32(post_doc + p + 64), d3 = ld_stream_u32(post_doc + p + 96);
-                    double u0 = load_val<KIND>(post_val, p), u1 = load_val<KIND>(post_val, p + 32);
-                    double u2 = load_val<KIND>(post_val, p + 64), u3 = load_val<KIND>(post_val, p + 96);
-                    apply_posting<KIND>(acc_w, d0 - my_doc0, u0, w_idf, w_q, w_idf64, w_q64);
-                    apply_posting<KIND>(acc_w, d1 - my_doc0, u1, w_idf, w_q, w_idf64, w_q64);
-                    apply_posting<KIND>(acc_w, d2 - my_doc0, u2, w_idf, w_q, w_idf64, w_q64);
-                    apply_posting<KIND>(acc_w, d3 - my_doc0, u3, w_idf, w_q, w_idf64, w_q64);
-                }
-                for (; p < end; p += 32) {
-                    uint32_t d = ld_stream_u32(post_doc + p);
-                    double u = load_val<KIND>(post_val, p);
-                    apply_posting<KIND>(acc_w, d - my_doc0, u, w_idf, w_q, w_idf64, w_q64);
-                }
-            } else {
-                for (uint32_t p = beg + lane; p < end; p += 32) {
-                    const uint32_t rel = __ldg(post_doc + p) - my_doc0;  // blocks are shared by the 8 warps: keep in L1
-                    if (rel < (uint32_t)sub) {
-                        double u = load_val<KIND>(post_val, p);
-                        apply_posting<KIND>(acc_w, rel, u, w_idf, w_q, w_idf64, w_q64);
-                    }
-                }
-            }
+            if (first) apply_term<KIND, true>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
+            else apply_term<KIND, false>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
+            first = false;
             __syncwarp();
         }
     }

@@ -32,6 +32,17 @@ def set_int8_mma(enabled: bool) -> None:
     _abi.lib.b2r_set_int8_mma(1 if enabled else 0)
 
 
+def set_int8_cluster(max_cluster: int) -> None:
+    """Profiling / test hook: largest thread-block cluster (TMA multicast group of query-tile CTAs) of the tcgen05
+    scan kernel; 1 disables clusters.  Results are identical."""
+    _abi.lib.b2r_set_int8_cluster(int(max_cluster))
+
+
+def set_bank_schedule(enabled: bool) -> None:
+    """Profiling / test hook: False makes later index builds keep dense segments doc-ascending."""
+    _abi.lib.b2r_set_bank_schedule(1 if enabled else 0)
+
+
 def set_int8_fused(mode) -> None:
     """Profiling / test hook: 0/False = plain chunked dense-tile + select path, 1/True = fused selection for
     batches of >= 512 queries (default), 2 = fused selection for every batch size."""

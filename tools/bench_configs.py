@@ -91,7 +91,12 @@ def run_int8(args):
     d8 = torch.randint(-127, 128, (n, dim), device=dev, dtype=torch.int8, generator=g)
     ds = torch.rand(n, device=dev, generator=g) + 0.01
     out = []
-    for nq in args.queries:
+    for nq, cl, fm in [(a, b, c) for a in args.queries for b in (args.clusters or [None])
+                       for c in (args.fused_modes or [None])]:
+        if cl is not None:
+            b200ret.set_int8_cluster(cl)
+        if fm is not None:
+            b200ret.set_int8_fused(fm)
         q8 = torch.randint(-127, 128, (nq, dim), device=dev, dtype=torch.int8, generator=g)
         qs = (torch.rand(nq, device=dev, generator=g) + 0.01) / 127
         ms = timed(lambda: b200ret.int8_scan_topk(q8, d8, qs, ds, k), steps=3, warmup=1)
@@ -99,6 +104,10 @@ def run_int8(args):
         rec = {"config": f"c5: INT8 {dim}-d exhaustive scan, {n} vectors, top-{k}", "queries": nq, "ms": ms,
                "queries_per_s": nq / (ms * 1e-3), "int8_tops": ops / (ms * 1e-3) / 1e12,
                "corpus_gbs": n * (dim + 4) / (ms * 1e-3) / 1e9}
+        if cl is not None:
+            rec["max_cluster"] = cl
+        if fm is not None:
+            rec["fused_mode"] = fm
         if nq <= 64 and n <= 2_000_000:    # parity spot check on the first query against exact integer math
             idx, val, _ = b200ret.int8_scan_topk(q8[:1], d8, qs[:1], ds, k)
             dots = (d8.to(torch.int32) * q8[0].to(torch.int32)).sum(1).to(torch.float64)
@@ -250,6 +259,10 @@ def main():
     ap.add_argument("--docs", type=int, default=None)
     ap.add_argument("--queries", type=int, nargs="+", default=[1, 64, 1024])
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--fused-modes", type=int, nargs="*", default=None,
+                    help="int8: sweep b2r_set_int8_fused (0 plain, 1 default gate, 2 fused for every batch size)")
+    ap.add_argument("--clusters", type=int, nargs="*", default=None,
+                    help="int8: sweep the thread-block cluster cap of the tcgen05 kernel (A/B measurement)")
     args = ap.parse_args()
     if args.docs is None:
         args.docs = {"int8": 2_000_000, "c3": 8_800_000, "c4": 2_200_000}[args.what]
