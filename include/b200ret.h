@@ -184,7 +184,8 @@ void b2r_set_int8_mma(int enabled);
  * chunk by TMA multicast) the tcgen05 kernel may use; 1 = no clusters. */
 void b2r_set_int8_cluster(int max_cluster);
 /* Test / profiling hook: 0 = b2r_int8_scan_topk uses the plain chunked "dense tile + select" path;
- * 1 = fused selection for batches of >= 512 queries (default); 2 = fused selection for every batch size. */
+ * otherwise (default) the fused-selection path: sampled threshold, f32 pre-filter + exact f64 check in the
+ * MMA epilogue, candidate lists, device-gated exact fallback. */
 void b2r_set_int8_fused(int enabled);
 /* Exhaustive INT8 scan with fused per-query top-k (never materialises [n_q, n_docs]). */
 int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim, int32_t k, size_t *bytes);

@@ -513,7 +513,7 @@ static int make_rowmajor_i8_map(CUtensorMap *map, const int8_t *base, int64_t n_
     return B2R_OK;
 }
 
-static int g_int8_cluster = 4;  // largest cluster the launch may use (1 = no multicast)
+static int g_int8_cluster = 2;  // largest cluster the launch may use (1 = no multicast); measured: 1 = 2 > 4, 8
 
 template <int OUT>
 static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
@@ -630,7 +630,7 @@ struct I8Fused {
 };
 static bool g_int8_fused = true;
 
-static int g_int8_fused_min_q = 512;  // below this the extra launches cost more than the score tile they save
+static int g_int8_fused_min_q = 1;  // measured: with the f32 pre-filter the fused path wins at every batch size
 
 static I8Fused i8_fused_plan(int32_t n_q, int64_t n_docs, int dim, int k, bool shape_ok) {
     I8Fused p = {};
@@ -657,11 +657,8 @@ static size_t i8_fused_bytes(const I8Fused &fp, int64_t nq, int k) {
            topk_keys_ws_bytes(nq, fp.cap, k) + 256;
 }
 
-// enabled: 0 = plain chunked path; 1 = fused path for batches of >= 512 queries (default); 2 = fused path always
-extern "C" void b2r_set_int8_fused(int enabled) {
-    g_int8_fused = enabled != 0;
-    g_int8_fused_min_q = enabled >= 2 ? 1 : 512;
-}
+// enabled: 0 = plain chunked "dense tile + select" path; otherwise the fused-selection path (default)
+extern "C" void b2r_set_int8_fused(int enabled) { g_int8_fused = enabled != 0; }
 
 extern "C" int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim, int32_t k, size_t *bytes) {
     B2R_CHECK_ARG(bytes && n_q >= 0 && n_docs >= 1 && k >= 1 && k <= B2R_TOPK_MAX_FAST,

@@ -19,6 +19,8 @@
 // result is exact for any corpus order; the gate is evaluated on the device, nothing synchronises.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b2r {
 
 // posting streams are read once per CTA: keep them out of L1 (the accumulators own the SM's L1/smem pipe)
@@ -162,7 +164,34 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     }
     __syncwarp();
     uint32_t zphase = 0;
-    // normally gridDim.y == n_y (one tile per CTA); the gated fallback launches few CTAs that walk the tiles
+    const int qs = q_ptr[q], qe = q_ptr[q + 1];
+    auto tile_of = [&](int y) -> int {
+        return tile_mode == SC_TILES_ALL ? y
+               : tile_mode == SC_TILES_SAMPLE ? y * tile_step
+                                              : y + y / (tile_step - 1) + 1;  // tiles with tile % step != 0
+    };
+    // A CTA walks several doc tiles (stride gridDim.y).  A query of <= 32 terms is staged ONCE, lane j keeping
+    // term j's weights and the base of its offset row; per tile only the two offsets of the warp's posting range
+    // are fetched, one tile ahead, so the dependent chain q_terms -> dense_id -> offsets -> postings is paid once
+    // per CTA instead of once per tile.
+    const bool staged = qe - qs <= 32;
+    const uint32_t *my_row = nullptr;  // dense: offsets per sub-tile; sparse: offsets per tile
+    float my_idf = 0.f, my_qw = 0.f;
+    int my_dense = 0;
+    uint32_t nxt_beg = 0, nxt_end = 0;
+    if (staged && lane < qe - qs) {
+        const int t = q_terms[qs + lane];
+        my_qw = q_weights[qs + lane];
+        my_idf = idf[t];
+        const int32_t did = dense_id[t];
+        my_dense = did >= 0;
+        my_row = my_dense ? dense_ptr + (size_t)did * dense_row + w : blk_ptr + (size_t)t * n_tiles;
+        if ((int)blockIdx.y < n_y) {
+            const size_t i0 = (size_t)tile_of(blockIdx.y) * (my_dense ? B2R_SUBTILES : 1);
+            nxt_beg = my_row[i0];
+            nxt_end = my_row[i0 + 1];
+        }
+    }
   for (int y = blockIdx.y; y < n_y; y += gridDim.y) {
     if (lane == 0) {  // clear my sub-tile's accumulators with one bulk copy; overlaps the term staging below
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar_a), "r"((uint32_t)(sub * 8))
@@ -173,36 +202,39 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             "l"(g_zero_page), "r"((uint32_t)(sub * 8)), "r"(zbar_a)
             : "memory");
     }
-    const int qs = q_ptr[q], qe = q_ptr[q + 1];
-    const int tile = tile_mode == SC_TILES_ALL ? y
-                     : tile_mode == SC_TILES_SAMPLE ? y * tile_step
-                                                    : y + y / (tile_step - 1) + 1;  // tiles with tile % step != 0
+    const int tile = tile_of(y);
     const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
     const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
+    uint32_t my_beg = nxt_beg, my_end = nxt_end;
+    if (staged && my_row != nullptr && y + (int)gridDim.y < n_y) {  // offsets of the next tile: used one iteration later
+        const size_t i1 = (size_t)tile_of(y + gridDim.y) * (my_dense ? B2R_SUBTILES : 1);
+        nxt_beg = my_row[i1];
+        nxt_end = my_row[i1 + 1];
+    }
 
     bool cleared = false;
     bool first = true;  // no term has touched this warp's sub-tile yet (warp-uniform)
 
     for (int j0 = qs; j0 < qe; j0 += 32) {
         const int nt = min(32, qe - j0);
-        // lane j stages term j0+j: posting range of this warp (dense) or of the whole tile block (sparse)
-        uint32_t my_beg = 0, my_end = 0;
-        float my_idf = 0.f, my_qw = 0.f;
-        int my_dense = 0;
-        if (lane < nt) {
-            const int t = q_terms[j0 + lane];
-            my_qw = q_weights[j0 + lane];
-            my_idf = idf[t];
-            const int32_t did = dense_id[t];
-            if (did >= 0) {
-                const uint32_t *row = dense_ptr + (size_t)did * dense_row + my_sub;
-                my_beg = row[0];
-                my_end = row[1];
-                my_dense = 1;
-            } else {
-                const size_t e = (size_t)t * n_tiles + tile;
-                my_beg = blk_ptr[e];
-                my_end = blk_ptr[e + 1];
+        if (!staged) {  // long query: lane j stages term j0+j for this tile (dense: my sub-tile; sparse: the tile block)
+            my_beg = my_end = 0;
+            my_dense = 0;
+            if (lane < nt) {
+                const int t = q_terms[j0 + lane];
+                my_qw = q_weights[j0 + lane];
+                my_idf = idf[t];
+                const int32_t did = dense_id[t];
+                if (did >= 0) {
+                    const uint32_t *row = dense_ptr + (size_t)did * dense_row + my_sub;
+                    my_beg = row[0];
+                    my_end = row[1];
+                    my_dense = 1;
+                } else {
+                    const size_t e = (size_t)t * n_tiles + tile;
+                    my_beg = blk_ptr[e];
+                    my_end = blk_ptr[e + 1];
+                }
             }
         }
         if (!cleared) {  // the staging loads above were issued before this wait
@@ -232,19 +264,28 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     } else {
         const uint64_t thr = o.thr_keys[(int64_t)ql * o.k + o.k - 1];
         const uint32_t thr_hi = (uint32_t)(thr >> 32);
-        // a document can only beat thr if its score is >= the threshold score (thr_hi == 0: no threshold yet)
-        const float thr_f = thr_hi ? unord_f32(thr_hi) : __int_as_float(0xff800000);
+        // A document can only beat thr if f32(acc) >= the threshold score.  f64 -> f32 conversions are slow
+        // (a 64-bit conversion pipe), so the 4096 accumulators are first compared in f64 against the f32
+        // value just below the threshold score: acc < pred(thr_f) implies f32(acc) <= pred(thr_f) < thr_f
+        // (rounding is monotone).  Only survivors are converted and keyed.  thr_hi == 0: no threshold yet.
+        // ordered encoding: -1 = next smaller f32; 0x7fffffff would be -0.0 (== +0.0 in the ranking): skip it;
+        // at or below -inf (0x007fffff) there is nothing smaller: no filter
+        uint32_t thr_ord = thr_hi > 0x007fffffu ? thr_hi - 1u : 0u;
+        if (thr_ord == 0x7fffffffu) thr_ord = 0x7ffffffeu;
+        const double thr_lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
         for (int i = lane * 2; i < sub; i += 64) {
-            double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
-            float f[2] = {__double2float_rn(a.x), __double2float_rn(a.y)};
+            const double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            if (a.x >= thr_lo || a.y >= thr_lo) {
+                const double av[2] = {a.x, a.y};
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t doc = my_doc0 + i + c;
-                if ((f[c] >= thr_f || thr_hi == 0) && doc < o.n_docs) {
-                    const uint64_t key = make_key(ord_f32(f[c]), o.doc_id_base + doc);
-                    if (key > thr) {
-                        const int slot = atomicAdd(o.cand_cnt + ql, 1);
-                        if (slot < o.cap) o.cand[(int64_t)ql * o.cap + slot] = key;
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t doc = my_doc0 + i + c;
+                    if (av[c] >= thr_lo && doc < o.n_docs) {
+                        const uint64_t key = make_key(ord_f32(__double2float_rn(av[c])), o.doc_id_base + doc);
+                        if (key > thr) {
+                            const int slot = atomicAdd(o.cand_cnt + ql, 1);
+                            if (slot < o.cap) o.cand[(int64_t)ql * o.cap + slot] = key;
+                        }
                     }
                 }
             }
@@ -281,13 +322,24 @@ struct ScoreLaunch {
     cudaStream_t st;
 };
 
+// doc tiles walked by one CTA of the scorer (B2R_SCORE_TILES_PER_CTA overrides it: tuning experiments only)
+static int tiles_per_cta_default() {
+    const char *e = getenv("B2R_SCORE_TILES_PER_CTA");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 64 ? v : 4;
+}
+static const int g_tiles_per_cta = tiles_per_cta_default();
+
 template <int OUT>
 static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
     if (nq == 0 || n_y == 0) return B2R_OK;
     const b2r_index *ix = L.ix;
     const size_t smem = (size_t)ix->tile_docs * sizeof(double);
     // a gated launch is expected to do nothing: keep its grid tiny (each CTA walks n_y / 4 tiles if it runs)
-    const int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : n_y;
+    // tiles per CTA: enough CTAs must remain to fill the GPU a few times over (148 SMs x 6 CTAs)
+    int per_cta = g_tiles_per_cta;
+    while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 6 * 4) per_cta >>= 1;
+    const int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
     dim3 grid((unsigned)nq, (unsigned)grid_y);
     if (ix->kind == B2R_KIND_BM25) {
         auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;

@@ -44,12 +44,12 @@ def set_bank_schedule(enabled: bool) -> None:
 
 
 def set_int8_fused(mode) -> None:
-    """Profiling / test hook: 0/False = plain chunked dense-tile + select path, 1/True = fused selection for
-    batches of >= 512 queries (default), 2 = fused selection for every batch size."""
+    """Profiling / test hook: 0/False = plain chunked dense-tile + select path, otherwise the fused-selection
+    path (default).  Results are identical."""
     _abi.lib.b2r_set_int8_fused(int(mode))
 
 
-__all__ = ["set_int8_mma", "set_int8_fused", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
+__all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_bank_schedule", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
            "int8_scan_topk"]
 

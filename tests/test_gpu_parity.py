@@ -156,14 +156,18 @@ def test_int8_fused_scan_equals_plain_and_survives_overflow(b2r, k):
     ds = rng.random(n).astype(np.float32) + 0.01
     d8_adv = d8.copy()
     d8_adv[((np.arange(n) // 128) % 16) == 0] = 0           # every sample tile scores exactly 0
-    for corpus in (d8, d8_adv):
-        b2r.set_int8_fused(2)            # fused path regardless of the batch size
+    # scales outside the range the epilogue's f32 pre-filter is proven for (it must then take the exact path),
+    # zero and negative scales (negative / zero thresholds)
+    ds_odd = rng.choice(np.array([0.0, 1e-20, 3e-16, 1.0, 0.37, -0.5, 1e16, 1e20], np.float32), n)
+    qs_odd = rng.choice(np.array([1 / 127, 0.0, 1e-20, -1e-3, 1e10, 0.02], np.float32), nq)
+    for corpus, qs, ds in ((d8, qs, ds), (d8_adv, qs, ds), (d8, qs_odd, ds_odd), (d8, qs, -ds)):
+        b2r.set_int8_fused(1)
         fi, fv, _ = b2r.int8_scan_topk(q8, corpus, qs, ds, k, doc_id_base=1000)
         b2r.set_int8_fused(0)
         pi, pv, _ = b2r.int8_scan_topk(q8, corpus, qs, ds, k, doc_id_base=1000)
         b2r.set_int8_fused(1)
         assert torch.equal(fi, pi) and torch.equal(fv, pv)
-        for q in (0, 64, nq - 1):
+        for q in (0, 1, 2, 3, 64, nq - 1):
             want = np_oracle.int8_dot_batch(q8[q:q + 1], corpus, qs[q:q + 1], ds)[0]
             wi, wv = np_oracle.topk_canonical(want, k)
             assert np.array_equal(fi[q].cpu().numpy(), wi + 1000)
@@ -354,6 +358,31 @@ def test_bm25_edge_queries(b2r):
     dup = indices.copy(); dup[indptr[5] + 1] = dup[indptr[5]]       # row 5 lists one term twice
     with pytest.raises(ValueError, match="twice"):
         b2r.TermMajorIndex.from_csr(data, dup, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=256)
+
+
+def test_long_queries_walk_several_tiles_per_cta(b2r):
+    """Queries of more than 32 terms are re-staged per tile while a CTA walks several doc tiles (the <= 32-term
+    queries of the other tests keep their terms in registers across tiles): both against the oracle."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab, k = 61_000, 4000, 10
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 40, seed=41)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    rng = np.random.default_rng(42)
+    qs = [(rng.choice(n_vocab, size=int(rng.integers(33, 70)), replace=False), rng.integers(1, 4, 70)[:0])
+          for _ in range(72)]
+    qs = [(t_, np.ones(len(t_), np.float32) * (1 + i % 3)) for i, (t_, _) in enumerate(qs)]
+    qs[5] = (np.arange(0, 32), np.ones(32, np.float32))              # exactly 32 terms: the staged path
+    q_ptr, q_terms, q_w = b2r.pack_queries(qs)
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=256)
+    wi, wv = _oracle_topk((data, indices, indptr, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, k)
+    for fused in (True, False):
+        b2r.set_fused_selection(fused)
+        try:
+            idx, val = ix.search(q_ptr, q_terms, q_w, k)
+        finally:
+            b2r.set_fused_selection(True)
+        assert np.array_equal(idx.cpu().numpy(), wi), fused
+        assert np.array_equal(_bits(val.cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv))), fused
 
 
 def test_sharded_merge_equals_single_index(b2r):
