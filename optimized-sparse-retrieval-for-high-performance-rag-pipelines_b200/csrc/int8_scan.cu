@@ -109,7 +109,8 @@ constexpr int MM_M = 128;        // documents per tile  = UMMA M = TMEM lanes
 constexpr int MM_N = 128;        // queries per tile    = UMMA N = TMEM columns (int32)
 constexpr int MM_KC = 128;       // bytes of K per shared-memory chunk = one 128B swizzle row
 constexpr int MM_UK = 32;        // bytes of K per tcgen05.mma kind::i8
-constexpr int MM_THREADS = 320;    // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int MM_EPI_WARPS = 16;   // 4 TMEM lane quadrants x 4 column groups of 32
+constexpr int MM_THREADS = 32 * (MM_EPI_WARPS + 2);  // warps 0-15 epilogue, warp 16 TMA producer, warp 17 MMA issuer
 constexpr int MM_MAX_KC = 6;     // dim <= 768
 constexpr int MM_CHUNK_BYTES = MM_M * MM_KC;  // 16 KB: [128 rows][128 B], 8-row x 128 B swizzle atoms
 
@@ -210,11 +211,12 @@ struct MmBars {
 };
 
 // Warp-specialised, persistent: CTA (x = query tile of 128, y) walks document tiles y, y+gridDim.y, ...
-//   warp 8 lane 0 : TMA producer  -- document tile K-chunks (128 docs x 128 B, SWIZZLE_128B) into a ring
-//   warp 9 lane 0 : MMA issuer    -- 4 x tcgen05.mma kind::i8 (M128 N128 K32) per chunk, accumulators in TMEM,
+//   warp 16 lane 0: TMA producer  -- document tile K-chunks (128 docs x 128 B, SWIZZLE_128B) into a ring
+//   warp 17 lane 0: MMA issuer    -- 4 x tcgen05.mma kind::i8 (M128 N128 K32) per chunk, accumulators in TMEM,
 //                                    double buffered (2 x 128 columns) so the epilogue overlaps the next tile
-//   warps 0-7     : epilogue      -- tcgen05.ld (one document row per thread; warp w reads TMEM lane quadrant
-//                                    w % 4 and column half w / 4), f64 scale chain, f32 stores
+//   warps 0-15    : epilogue      -- tcgen05.ld (one document row per thread; warp w reads TMEM lane quadrant
+//                                    w % 4 and the 32 columns of group w / 4); DENSE: f64 scale chain, f32
+//                                    stores; FUSED: f32 pre-filter, exact chain for the survivors only
 // Query tiles are the fast grid dimension and form a thread-block cluster (up to 8 CTAs): every document
 // K-chunk is fetched from L2 ONCE per cluster and TMA-multicast into the same ring slot of every CTA (the
 // CTAs take turns issuing), which divides the L2->SM operand traffic -- the limiter of a 128 x 128 tile --
@@ -282,7 +284,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars.tfull[i], 1);
-            mbar_init(&bars.tempty[i], 8);  // one arrival per epilogue warp
+            mbar_init(&bars.tempty[i], MM_EPI_WARPS);  // one arrival per epilogue warp
         }
         mbar_init(&bars.bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -314,7 +316,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 8) {
+    if (warp == MM_EPI_WARPS) {
         if (lane == 0) {  // ---- TMA producer
             mbar_expect_tx(&bars.bfull, (uint32_t)(n_kc * MM_CHUNK_BYTES));
             for (int kc = 0; kc < n_kc; ++kc) tma_load_2d(sB + kc * MM_CHUNK_BYTES, &map_q, kc * MM_KC, q0, &bars.bfull);
@@ -341,7 +343,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == MM_EPI_WARPS + 1) {
         if (lane == 0) {  // ---- MMA issuer
             const uint32_t idesc = umma_idesc_s8(MM_M, MM_N);
             mbar_wait(smem_u32(&bars.bfull), 0);
@@ -376,21 +378,26 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
             }
         }
         __syncwarp();
-    } else {  // ---- epilogue warps 0..7: TMEM lane quadrant = warp % 4 (document rows), column half = warp / 4
-        const int quad = warp & 3, half = warp >> 2;
+    } else {  // ---- epilogue warps: TMEM lane quadrant = warp % 4 (document rows), column group = warp / 4
+        const int quad = warp & 3, c0 = (warp >> 2) * 32;
         int acc = 0;
         uint32_t acc_ph = 0;
+        auto scale_of = [&](int64_t t) -> float {  // scale of this thread's document row in logical tile t
+            const int64_t d = tile_of(t) * MM_M + quad * 32 + lane;
+            return (t < n_tiles && d < n_docs) ? __ldg(d_scale + d) : 0.0f;
+        };
+        float dsf_next = scale_of(blockIdx.y);
         for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
             const int64_t doc = tile_of(t) * MM_M + quad * 32 + lane;
             const bool doc_ok = doc < n_docs;
-            const float dsf = doc_ok ? d_scale[doc] : 0.0f;
+            const float dsf = dsf_next;
+            dsf_next = scale_of(t + gridDim.y);  // one tile ahead: its latency hides behind this tile's work
             const double ds = (double)dsf;
             const bool ds_sane = fabsf(dsf) >= 1e-15f && fabsf(dsf) <= 1e15f;
             mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = half * 64 + cc * 32;
+            {
+                const int cc = 1;  // (one 32-column group per warp: its only load is also its last)
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * MM_N + c0);
                 asm volatile(
@@ -404,7 +411,9 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                       "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == 1) {  // this warp's share of the accumulator is in registers: hand it back
+                // DENSE: this warp's share of the accumulator is in registers after the second load: hand it back.
+                // FUSED re-reads single columns of survivors from TMEM and releases the buffer after that.
+                if (OUT == MM_OUT_DENSE && cc == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.tempty[acc]);
@@ -428,7 +437,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                             }
                         }
                     }
-                } else if (doc_ok) {
+                } else {
                     // 1. f32 pre-filter over the 32 columns: one bit per column that may beat its threshold
                     uint32_t hit = 0;
 #pragma unroll
@@ -438,25 +447,32 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                         hit |= (p < f.y) ? 0u : (1u << j);  // NaN passes
                     }
                     if (!ds_sane) hit = 0xffffffffu;
-                    // 2. exact f64 chain for the survivors only (8 columns at a time: most groups are empty)
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if ((hit >> (8 * g)) & 0xffu) {
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) {
-                                const int j = 8 * g + jj;
-                                if ((hit >> j) & 1u) {
-                                    const float sc = __double2float_rn(
-                                        __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds));
-                                    const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
-                                    if (key > thr_key_s[c0 + j]) {
-                                        const int q = q0 + c0 + j;
-                                        const int slot = atomicAdd(o.cand_cnt + q, 1);
-                                        if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
-                                    }
-                                }
+                    if (!doc_ok) hit = 0;
+                    // 2. exact f64 chain for the survivors only.  The loop runs over the columns in which ANY
+                    // lane has a survivor (warp-uniform, usually none or one) and re-reads that column from TMEM,
+                    // so the unrolled filter above stays branch-free and the rare path is a small rolled loop.
+                    uint32_t cols = __reduce_or_sync(0xffffffffu, hit);
+                    while (cols) {
+                        const int j = __ffs(cols) - 1;
+                        cols &= cols - 1;
+                        uint32_t dot;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dot) : "r"(taddr + (uint32_t)j));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if ((hit >> j) & 1u) {
+                            const float sc =
+                                __double2float_rn(__dmul_rn(__dmul_rn((double)(int32_t)dot, qs_s[c0 + j]), ds));
+                            const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
+                            if (key > thr_key_s[c0 + j]) {
+                                const int q = q0 + c0 + j;
+                                const int slot = atomicAdd(o.cand_cnt + q, 1);
+                                if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
                             }
                         }
+                    }
+                    if (cc == 1) {  // done with this accumulator buffer
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars.tempty[acc]);
                     }
                 }
             }
