@@ -302,13 +302,7 @@ def run_b200(args):
     n_samp, t_step, cap = C.c_int32(0), C.c_int32(0), C.c_int32(0)
     lib.b2r_fused_plan(C.byref(ix._desc), k, C.byref(n_samp), C.byref(t_step), C.byref(cap))
     fused = n_samp.value > 0
-    rows = np.repeat(np.arange(hi - lo, dtype=np.int64), np.diff(w["indptr"][lo:hi + 1]))
-    if fused:   # postings and docs of the tiles the fused launch covers (tile % step != 0)
-        in_rest = ((rows // args.tile_docs) % t_step.value) != 0
-        df_k = np.bincount(w["indices"][s:e][in_rest], minlength=w["n_vocab"])
-        docs_k = int((((np.arange(hi - lo) // args.tile_docs) % t_step.value) != 0).sum())
-    else:
-        df_k, docs_k = df_local, hi - lo
+    df_k = df_local          # the fused launch scores every tile of the shard (the sample launch comes on top)
     postings = int(df_local[w["q_terms"]].sum())
     postings_k = int(df_k[w["q_terms"]].sum())
     lib.b2r_set_profiling(1)
@@ -354,7 +348,8 @@ def run_b200(args):
                        "l2": "inputs exceed L2: per step the index shard (%.2f GB) plus a %.2f GB score tile stream "
                              "through HBM; no flush needed" % (ix.device_bytes() / 1e9, nq * ix.padded_docs * 4 / 1e9),
                        "postings_touched_per_step_rank0": postings, "cuda_graph_replay": graphed,
-                       "selection": ("fused: threshold from every %dth tile, candidate cap %d" % (t_step.value, cap.value))
+                       "selection": ("fused: threshold = k-th largest group maximum of every %dth tile, all tiles scored with the "
+                                     "candidate epilogue, cap %d" % (t_step.value, cap.value))
                        if fused else "plain: score vector + streaming select"},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -103,9 +103,12 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
                      const TopkOpts &opts = TopkOpts());
 size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k);       // for topk_scores_rows
 size_t topk_keys_ws_bytes(int64_t n_rows, int64_t n, int32_t k);  // for topk_keys_rows
-// cand[q][0..k) = sample winners, cand_cnt[q] = k (score.cu)
-int seed_candidates(const uint64_t *sample_keys, int nq, int k, int cap, uint64_t *cand, int32_t *cand_cnt,
-                    cudaStream_t st);
+// thr_out[row] = key with the score of the k-th largest of the n_groups f32 group maxima of the row and doc
+// bits 0 (every document with at least that score beats it); 0 when fewer than k maxima are finite.
+// lower = true: the maxima are f32 approximations within 2^-22 of the exact scores -- lower the threshold by
+// 2^-20 relative so that it stays a valid bound for the exact scores (INT8 scan).
+int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
+                  uint64_t *thr_out, cudaStream_t st);
 int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
                 int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st);
 

@@ -222,19 +222,21 @@ struct MmBars {
 // CTAs take turns issuing), which divides the L2->SM operand traffic -- the limiter of a 128 x 128 tile --
 // by the cluster size.  A ring slot is reused only after the MMAs of ALL CTAs of the cluster have read it
 // (multicast tcgen05.commit onto every CTA's `empty` barrier, arrival count = cluster size).
-enum { MM_OUT_DENSE = 0, MM_OUT_FUSED = 1 };
-enum { MM_TILES_ALL = 0, MM_TILES_SAMPLE = 1, MM_TILES_REST = 2 };
+enum { MM_OUT_DENSE = 0, MM_OUT_FUSED = 1, MM_OUT_MAXIMA = 2 };
+enum { MM_TILES_ALL = 0, MM_TILES_SAMPLE = 1 };
+constexpr int MM_MAX_GROUPS = 148 * MM_M;  // MAXIMA: one running maximum per (CTA row y, document row of the tile)
 
 struct MmOut {
     // DENSE: f32 scores, column = logical tile * 128 + row (logical == actual unless a sample is being scored)
+    // MAXIMA: f32 approximate group maxima, column = blockIdx.y * 128 + row (one group = the documents a
+    //         thread sees while its CTA walks the sample tiles)
     float *out;
     int64_t out_stride;
     // optional gate (both epilogues): the CTA runs only if some query of its tile has gate[q] > gate_cap
     const int32_t *gate;
     int32_t gate_cap;
-    // FUSED: keep only documents whose key beats thr_keys[q*k + k-1]
+    // FUSED: keep only documents whose key beats thr_keys[q] (0 = no threshold)
     const uint64_t *thr_keys;
-    int32_t k;
     uint64_t *cand;      // [n_q, cap]
     int32_t *cand_cnt;   // [n_q]
     int32_t cap;
@@ -259,7 +261,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
     const int q0 = blockIdx.x * MM_N;
     const int64_t n_tiles = n_logical;  // logical tiles this launch covers; tile_of() maps them to document tiles
     auto tile_of = [&](int64_t y) -> int64_t {
-        return tile_mode == MM_TILES_ALL ? y : tile_mode == MM_TILES_SAMPLE ? y * tile_step : y + y / (tile_step - 1) + 1;
+        return tile_mode == MM_TILES_ALL ? y : y * tile_step;
     };
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
@@ -293,7 +295,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
         const bool qv = q0 + tid < n_q;
         qs_s[tid] = qv ? (double)q_scale[q0 + tid] : 0.0;
         if (OUT == MM_OUT_FUSED) {
-            const uint64_t thr = qv ? o.thr_keys[(int64_t)(q0 + tid) * o.k + o.k - 1] : ~0ull;
+            const uint64_t thr = qv ? o.thr_keys[q0 + tid] : ~0ull;
             const uint32_t hi = (uint32_t)(thr >> 32);
             thr_key_s[tid] = thr;
             // Pre-filter in f32 (the exact f64 chain costs two 64-bit conversions per output, which paces the
@@ -308,6 +310,10 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                               : __int_as_float(0xff800000);
             if (!qv) lo_f = __int_as_float(0x7f800000);  // no query in this column: nothing passes
             flt_s[tid] = make_float2(qf, lo_f);
+        } else if (OUT == MM_OUT_MAXIMA) {  // an odd scale gives NaN products, which fmaxf ignores
+            const float qf = qv ? q_scale[q0 + tid] : 0.0f;
+            const bool sane = qv && fabsf(qf) >= 1e-15f && fabsf(qf) <= 1e15f;
+            flt_s[tid] = make_float2(sane ? qf : __int_as_float(0x7fc00000), 0.0f);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -387,6 +393,9 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
             return (t < n_tiles && d < n_docs) ? __ldg(d_scale + d) : 0.0f;
         };
         float dsf_next = scale_of(blockIdx.y);
+        float runmax[OUT == MM_OUT_MAXIMA ? 32 : 1];
+#pragma unroll
+        for (int j = 0; j < (OUT == MM_OUT_MAXIMA ? 32 : 1); ++j) runmax[j] = __int_as_float(0xff800000);
         for (int64_t t = blockIdx.y; t < n_tiles; t += gridDim.y) {
             const int64_t doc = tile_of(t) * MM_M + quad * 32 + lane;
             const bool doc_ok = doc < n_docs;
@@ -413,7 +422,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 // DENSE: this warp's share of the accumulator is in registers after the second load: hand it back.
                 // FUSED re-reads single columns of survivors from TMEM and releases the buffer after that.
-                if (OUT == MM_OUT_DENSE && cc == 1) {
+                if (OUT != MM_OUT_FUSED && cc == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.tempty[acc]);
@@ -435,6 +444,16 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                                 const double sc = __dmul_rn(__dmul_rn((double)(int32_t)v[j], qs_s[c0 + j]), ds);
                                 optr[(int64_t)j * o.out_stride] = __double2float_rn(sc);
                             }
+                        }
+                    }
+                } else if (OUT == MM_OUT_MAXIMA) {
+                    // threshold sample: running maximum of the f32 approximation p = fl(fl(dot * qs) * ds) per
+                    // (thread = document row, query column); rows with an odd scale stay out of it
+                    if (doc_ok && ds_sane) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float p = __fmul_rn(__fmul_rn((float)(int32_t)v[j], flt_s[c0 + j].x), dsf);
+                            runmax[j] = fmaxf(runmax[j], p);
                         }
                     }
                 } else {
@@ -480,6 +499,12 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                 acc = 0;
                 acc_ph ^= 1;
             }
+        }
+        if (OUT == MM_OUT_MAXIMA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (q0 + c0 + j < n_q)
+                    o.out[(int64_t)(q0 + c0 + j) * o.out_stride + (int64_t)blockIdx.y * MM_M + quad * 32 + lane] = runmax[j];
         }
     }
 
@@ -534,7 +559,7 @@ static int g_int8_cluster = 2;  // largest cluster the launch may use (1 = no mu
 template <int OUT>
 static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
                            const float *ds, int tile_mode, int tile_step, int64_t n_logical, const MmOut &o,
-                           cudaStream_t st) {
+                           cudaStream_t st, int *gy_out = nullptr) {
     if (n_q == 0 || n_logical == 0) return B2R_OK;
     const int n_kc = dim / MM_KC;
     int n_stages = (200 * 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
@@ -575,6 +600,7 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
     if (gy < 1) gy = 1;
     if (gy > n_logical) gy = n_logical;
     cfg.gridDim = dim3((unsigned)gx, (unsigned)gy);
+    if (gy_out) *gy_out = (int)gy;
     B2R_CUDA(cudaLaunchKernelEx(&cfg, int8_mma_kernel<OUT>, map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, tile_mode,
                                 tile_step, n_logical, o));
     B2R_LAUNCH_CHECK();
@@ -642,35 +668,26 @@ extern "C" int b2r_int8_dot_batch(const int8_t *q8, int32_t n_q, const int8_t *d
 struct I8Fused {
     bool on;
     int step, cap;
-    int64_t n_tiles, n_sample, n_rest, sample_cols, sample_valid;
+    int64_t n_tiles, n_sample;
 };
 static bool g_int8_fused = true;
-
-static int g_int8_fused_min_q = 1;  // measured: with the f32 pre-filter the fused path wins at every batch size
 
 static I8Fused i8_fused_plan(int32_t n_q, int64_t n_docs, int dim, int k, bool shape_ok) {
     I8Fused p = {};
     p.n_tiles = (n_docs + MM_M - 1) / MM_M;
-    p.on = g_int8_fused && g_int8_use_mma && shape_ok && k <= 128 && p.n_tiles >= 256 && dim > 0 &&
-           n_q >= g_int8_fused_min_q;
+    // >= 256 tiles: the first sample tiles are full, so at least 128 >= k group maxima exist
+    p.on = g_int8_fused && g_int8_use_mma && shape_ok && k <= 128 && p.n_tiles >= 256 && dim > 0 && n_q >= 1;
     if (!p.on) return p;
-    p.step = k <= 16 ? 32 : 16;
+    p.step = k <= 16 ? 32 : 16;  // a query collects ~ k * step candidates (sigma ~ sqrt(k) * step)
     p.cap = k <= 16 ? 1024 : 4096;
     p.n_sample = (p.n_tiles + p.step - 1) / p.step;
-    p.n_rest = p.n_tiles - p.n_sample;
-    p.sample_cols = p.n_sample * MM_M;
-    int64_t last_valid = n_docs - (p.n_sample - 1) * p.step * MM_M;
-    if (last_valid > MM_M) last_valid = MM_M;
-    p.sample_valid = (p.n_sample - 1) * MM_M + last_valid;
-    if (p.sample_valid < k) p.on = false;
     return p;
 }
 
 static size_t i8_fused_bytes(const I8Fused &fp, int64_t nq, int k) {
     if (!fp.on) return 0;
-    return align_up((size_t)nq * fp.sample_cols * 4, 256) + topk_ws_bytes(nq, fp.sample_valid, k) +
-           align_up((size_t)nq * k * 8, 256) + align_up((size_t)nq * fp.cap * 8, 256) + align_up((size_t)nq * 4, 256) +
-           topk_keys_ws_bytes(nq, fp.cap, k) + 256;
+    return align_up((size_t)nq * MM_MAX_GROUPS * 4, 256) + align_up((size_t)nq * 8, 256) +
+           align_up((size_t)nq * fp.cap * 8, 256) + align_up((size_t)nq * 4, 256) + topk_keys_ws_bytes(nq, fp.cap, k) + 256;
 }
 
 // enabled: 0 = plain chunked "dense tile + select" path; otherwise the fused-selection path (default)
@@ -726,42 +743,37 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
     TopkOpts gate;  // empty unless the fused path ran: then only overflowed queries take the dense path below
     const I8Fused fp = i8_fused_plan(n_q, n_docs, dim, k, mma_shape_ok(dim, q8, d8));
     if (fp.on) {
-        float *samp = static_cast<float *>(carve((size_t)n_q * fp.sample_cols * 4));
-        const size_t tks_bytes = topk_ws_bytes(n_q, fp.sample_valid, k);
-        void *tks = carve(tks_bytes);
-        uint64_t *samp_keys = static_cast<uint64_t *>(carve((size_t)n_q * k * 8));
+        float *maxima = static_cast<float *>(carve((size_t)n_q * MM_MAX_GROUPS * 4));
+        uint64_t *thr = static_cast<uint64_t *>(carve((size_t)n_q * 8));
         uint64_t *cand = static_cast<uint64_t *>(carve((size_t)n_q * fp.cap * 8));
         int32_t *cand_cnt = static_cast<int32_t *>(carve((size_t)n_q * 4));
         const size_t tkc_bytes = topk_keys_ws_bytes(n_q, fp.cap, k);
         void *tkc = carve(tkc_bytes);
-        // 1. exact top-k of every step-th 128-document tile
+        // 1. threshold: every step-th 128-document tile is scanned with the MAXIMA epilogue (f32 approximation,
+        //    one running maximum per thread and query); the k-th largest group maximum, lowered by the
+        //    approximation margin, is a lower bound of the k-th best exact score
         MmOut so = {};
-        so.out = samp;
-        so.out_stride = fp.sample_cols;
-        int rc = launch_int8_mma<MM_OUT_DENSE>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_SAMPLE, fp.step,
-                                               fp.n_sample, so, st);
+        so.out = maxima;
+        so.out_stride = MM_MAX_GROUPS;
+        int gy = 0;
+        int rc = launch_int8_mma<MM_OUT_MAXIMA>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_SAMPLE, fp.step,
+                                                fp.n_sample, so, st, &gy);
         if (rc) return rc;
-        TopkOpts map;
-        map.chunk_shift = 7;  // 128-document tiles
-        map.chunk_stride = (uint32_t)fp.step * (uint32_t)MM_M;
-        rc = topk_scores_rows(samp, n_q, fp.sample_valid, fp.sample_cols, k, doc_id_base, samp_keys, tks, tks_bytes, st,
-                              map);
+        rc = kth_of_maxima(maxima, n_q, (int64_t)gy * MM_M, MM_MAX_GROUPS, k, true, thr, st);
         if (rc) return rc;
-        // 2. candidate lists seeded with the sample winners; 3. scan the rest, keep what beats the threshold
+        // 2. scan every tile, keep the documents whose exact key reaches the threshold
         B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)n_q * fp.cap * 8, st));
-        rc = seed_candidates(samp_keys, n_q, k, fp.cap, cand, cand_cnt, st);
-        if (rc) return rc;
+        B2R_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)n_q * 4, st));
         MmOut fo = {};
-        fo.thr_keys = samp_keys;
-        fo.k = k;
+        fo.thr_keys = thr;
         fo.cand = cand;
         fo.cand_cnt = cand_cnt;
         fo.cap = fp.cap;
         fo.doc_id_base = (uint32_t)doc_id_base;
-        rc = launch_int8_mma<MM_OUT_FUSED>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_REST, fp.step,
-                                           fp.n_rest, fo, st);
+        rc = launch_int8_mma<MM_OUT_FUSED>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_ALL, 1, fp.n_tiles, fo,
+                                           st);
         if (rc) return rc;
-        // 4. top-k of (sample winners + candidates)
+        // 3. exact top-k of the candidates; overflowed queries fall through to the gated exhaustive path
         rc = topk_keys_rows(cand, n_q, fp.cap, fp.cap, fp.cap, 0, k, keys, tkc, tkc_bytes, st);
         if (rc) return rc;
         gate.gate = cand_cnt;

@@ -9,14 +9,15 @@
 // query index fastest, so CTAs resident at the same time work on the same doc tile and share its
 // posting blocks through L2; HBM sees each posting once per batch.
 //
-// Two epilogues.  DENSE writes the f32 score vector (the reference's return value).  FUSED is the
-// search path: nothing is written but the few documents that beat a per-query threshold, appended to
-// a small candidate list.  The threshold is the exact k-th best key of a strided sample of doc tiles
-// (every 32nd / 16th tile, scored with the DENSE epilogue into a compact buffer and selected exactly), so
-// it is a valid lower bound of the final k-th best and the final top-k is the top-k of
-// (sample winners + candidates).  A query whose candidate list overflows is rescored exhaustively
-// by the gated DENSE + top-k kernels that follow (they exit at once for every other query), so the
-// result is exact for any corpus order; the gate is evaluated on the device, nothing synchronises.
+// Three epilogues.  DENSE writes the f32 score vector (the reference's return value).  MAXIMA and FUSED are
+// the search path, which never materialises scores: (1) every 64th / 16th doc tile is scored with the
+// MAXIMA epilogue, which emits one maximum per lane (a group of <= tile_docs/256 documents); the k-th largest
+// of those group maxima is a lower bound T of the k-th best score of the whole shard (k groups, hence k
+// documents, reach it).  (2) ALL tiles are scored with the FUSED epilogue, which appends the few documents
+// whose key beats T to a per-query candidate list; the exact top-k is the top-k of that list.  A query whose
+// list overflows is rescored exhaustively by the gated DENSE + top-k kernels that follow (they exit at once
+// for every other query), so the result is exact for any corpus order; the gate is evaluated on the device,
+// nothing synchronises.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -120,18 +121,19 @@ __device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end
 // only synchronisation is __syncwarp: no CTA barrier, no atomics, no load imbalance between warps
 // (a dense term's postings are split by sub-tile through dense_ptr; a sparse term's small block is
 // scanned by every warp, each keeping the postings that fall in its range).
-enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1 };
-enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1, SC_TILES_REST = 2 };
+enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1, SC_OUT_MAXIMA = 2 };
+enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1 };
+constexpr int SC_GROUPS_PER_TILE = 32 * B2R_SUBTILES;  // MAXIMA: one group maximum per lane
 
 struct ScoreOut {
-    // DENSE
-    float *scores;          // [queries, scores_stride]; column = out_tile * tile_docs + doc in tile
+    // DENSE: scores[queries, scores_stride], column = out_tile * tile_docs + doc in tile
+    // MAXIMA: scores[queries, scores_stride], column = out_tile * SC_GROUPS_PER_TILE + warp * 32 + lane
+    float *scores;
     int64_t scores_stride;
     const int32_t *gate;    // optional: run only for queries with gate[q_local] > gate_cap
     int32_t gate_cap;
     // FUSED
-    const uint64_t *thr_keys;  // [queries, k]: sample winners, ranked; threshold = thr_keys[q*k + k-1]
-    int32_t k;
+    const uint64_t *thr_keys;  // [queries]: keep documents whose key is > thr_keys[q] (0 = no threshold)
     uint64_t *cand;         // [queries, cap]
     int32_t *cand_cnt;      // [queries]
     int32_t cap;
@@ -166,9 +168,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     uint32_t zphase = 0;
     const int qs = q_ptr[q], qe = q_ptr[q + 1];
     auto tile_of = [&](int y) -> int {
-        return tile_mode == SC_TILES_ALL ? y
-               : tile_mode == SC_TILES_SAMPLE ? y * tile_step
-                                              : y + y / (tile_step - 1) + 1;  // tiles with tile % step != 0
+        return tile_mode == SC_TILES_ALL ? y : y * tile_step;
     };
     // A CTA walks several doc tiles (stride gridDim.y).  A query of <= 32 terms is staged ONCE, lane j keeping
     // term j's weights and the base of its offset row; per tile only the two offsets of the warp's posting range
@@ -261,8 +261,18 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
             *reinterpret_cast<float2 *>(out + i) = make_float2(__double2float_rn(a.x), __double2float_rn(a.y));
         }
+    } else if (OUT == SC_OUT_MAXIMA) {
+        // one maximum per lane over the (valid) documents it reads; f32(max) == max(f32): rounding is monotone
+        double m = -__longlong_as_double(0x7ff0000000000000ll);
+        for (int i = lane * 2; i < sub; i += 64) {
+            const double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            const uint32_t doc = my_doc0 + i;
+            if (doc < o.n_docs) m = fmax(m, a.x);
+            if (doc + 1 < o.n_docs) m = fmax(m, a.y);
+        }
+        o.scores[(int64_t)ql * o.scores_stride + (int64_t)y * SC_GROUPS_PER_TILE + w * 32 + lane] = __double2float_rn(m);
     } else {
-        const uint64_t thr = o.thr_keys[(int64_t)ql * o.k + o.k - 1];
+        const uint64_t thr = o.thr_keys[ql];
         const uint32_t thr_hi = (uint32_t)(thr >> 32);
         // A document can only beat thr if f32(acc) >= the threshold score.  f64 -> f32 conversions are slow
         // (a 64-bit conversion pipe), so the 4096 accumulators are first compared in f64 against the f32
@@ -295,24 +305,6 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
   }  // tile loop
-}
-
-// cand[q][0..k) = sample winners, cand_cnt[q] = k (the rest of cand was zeroed by a memset)
-__global__ void seed_candidates_kernel(const uint64_t *__restrict__ sample_keys, int nq, int k, int cap,
-                                       uint64_t *__restrict__ cand, int32_t *__restrict__ cand_cnt) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq * k) return;
-    int q = i / k, j = i - q * k;
-    cand[(int64_t)q * cap + j] = sample_keys[i];
-    if (j == 0) cand_cnt[q] = k;
-}
-
-int seed_candidates(const uint64_t *sample_keys, int nq, int k, int cap, uint64_t *cand, int32_t *cand_cnt,
-                    cudaStream_t st) {
-    if (nq == 0) return B2R_OK;
-    seed_candidates_kernel<<<(nq * k + 255) / 256, 256, 0, st>>>(sample_keys, nq, k, cap, cand, cand_cnt);
-    B2R_LAUNCH_CHECK();
-    return B2R_OK;
 }
 
 struct ScoreLaunch {
@@ -383,27 +375,23 @@ static cudaEvent_t g_ev[2] = {nullptr, nullptr};
 struct FusedPlan {
     bool on;
     int step;  // every step-th doc tile forms the threshold sample
-    int n_sample, n_rest, cap, shift;
-    int64_t sample_cols, sample_valid;
+    int n_sample, cap;
+    int64_t n_groups;  // group maxima per query = n_sample * SC_GROUPS_PER_TILE
 };
 
 static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
     FusedPlan p = {};
     p.on = g_fused_enabled && !want_scores && k >= 1 && k <= FUSED_MAX_K && ix->n_tiles >= FUSED_MIN_TILES;
     if (!p.on) return p;
-    // expected candidates ~ k * (step - 1) (negative-binomial tail); the list also holds the k sample winners
-    p.step = k <= 16 ? 32 : 16;
-    p.cap = k <= 16 ? 1024 : 4096;
+    // The threshold is (about) the k-th best of a 1/step sample, so a query collects ~ k * step candidates
+    // (negative-binomial: sigma ~ sqrt(k) * step); the caps are > 6 sigma above that.
+    p.step = k <= 16 ? 64 : 16;
+    p.cap = k <= 16 ? 2048 : 4096;
     p.n_sample = (ix->n_tiles + p.step - 1) / p.step;
-    p.n_rest = ix->n_tiles - p.n_sample;
-    p.shift = 0;
-    while ((1 << p.shift) < ix->tile_docs) ++p.shift;
-    p.sample_cols = (int64_t)p.n_sample * ix->tile_docs;
-    const int64_t last_tile = (int64_t)(p.n_sample - 1) * p.step;
-    int64_t last_valid = ix->n_docs - last_tile * ix->tile_docs;
-    if (last_valid > ix->tile_docs) last_valid = ix->tile_docs;
-    p.sample_valid = (int64_t)(p.n_sample - 1) * ix->tile_docs + last_valid;
-    if (p.sample_valid < k) p.on = false;
+    p.n_groups = (int64_t)p.n_sample * SC_GROUPS_PER_TILE;
+    // tile 0 is full (n_tiles >= 8) and holds min(tile_docs / 2, 256) non-empty groups
+    const int groups_tile0 = ix->tile_docs / 2 < SC_GROUPS_PER_TILE ? ix->tile_docs / 2 : SC_GROUPS_PER_TILE;
+    if (groups_tile0 < k) p.on = false;
     return p;
 }
 
@@ -411,9 +399,9 @@ static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
 static size_t pass_bytes(const b2r_index *ix, const FusedPlan &fp, int64_t qc, int k) {
     const size_t full = align_up((size_t)padded_docs(ix) * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k);
     if (!fp.on) return full;
-    return full + align_up((size_t)fp.sample_cols * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, fp.sample_valid, k) +
-           align_up((size_t)qc * k * 8, 256) + align_up((size_t)qc * fp.cap * 8, 256) + align_up((size_t)qc * 4, 256) +
-           topk_keys_ws_bytes(qc, fp.cap, k) + 256;
+    return full + align_up((size_t)fp.n_groups * 4 * (size_t)qc, 256) + align_up((size_t)qc * 8, 256) +
+           align_up((size_t)qc * fp.cap * 8, 256) + align_up((size_t)qc * 4, 256) + topk_keys_ws_bytes(qc, fp.cap, k) +
+           256;
 }
 
 }  // namespace b2r
@@ -532,16 +520,14 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
     float *full = static_cast<float *>(carve((size_t)pad * 4 * (size_t)qc));
     const size_t tk_full_bytes = topk_ws_bytes(qc, ix->n_docs, k);
     void *tk_full = carve(tk_full_bytes);
-    float *samp = nullptr;
-    void *tk_samp = nullptr, *tk_cand = nullptr;
-    uint64_t *samp_keys = nullptr, *cand = nullptr;
+    float *maxima = nullptr;
+    void *tk_cand = nullptr;
+    uint64_t *thr = nullptr, *cand = nullptr;
     int32_t *cand_cnt = nullptr;
-    size_t tk_samp_bytes = 0, tk_cand_bytes = 0;
+    size_t tk_cand_bytes = 0;
     if (fp.on) {
-        samp = static_cast<float *>(carve((size_t)fp.sample_cols * 4 * (size_t)qc));
-        tk_samp_bytes = topk_ws_bytes(qc, fp.sample_valid, k);
-        tk_samp = carve(tk_samp_bytes);
-        samp_keys = static_cast<uint64_t *>(carve((size_t)qc * k * 8));
+        maxima = static_cast<float *>(carve((size_t)fp.n_groups * 4 * (size_t)qc));
+        thr = static_cast<uint64_t *>(carve((size_t)qc * 8));
         cand = static_cast<uint64_t *>(carve((size_t)qc * fp.cap * 8));
         cand_cnt = static_cast<int32_t *>(carve((size_t)qc * 4));
         tk_cand_bytes = topk_keys_ws_bytes(qc, fp.cap, k);
@@ -553,39 +539,33 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
         uint64_t *kout = keys + q0 * k;
         TopkOpts gate;
         if (fp.on) {
-            // 1. threshold sample: every step-th tile, exact top-k of the sample
+            // 1. threshold: group maxima of every step-th tile, then the k-th largest of them per query
             ScoreOut so = {};
-            so.scores = samp;
-            so.scores_stride = fp.sample_cols;
-            rc = launch_score<SC_OUT_DENSE>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
+            so.scores = maxima;
+            so.scores_stride = fp.n_groups;
+            so.n_docs = (uint32_t)ix->n_docs;
+            rc = launch_score<SC_OUT_MAXIMA>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
             if (rc) return rc;
-            TopkOpts map;
-            map.chunk_shift = fp.shift;
-            map.chunk_stride = (uint32_t)fp.step * (uint32_t)ix->tile_docs;
-            rc = topk_scores_rows(samp, nq, fp.sample_valid, fp.sample_cols, k, ix->doc_id_base, samp_keys, tk_samp,
-                                  tk_samp_bytes, st, map);
+            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, thr, st);
             if (rc) return rc;
-            // 2. candidate lists seeded with the sample winners
+            // 2. every tile: score, keep only the documents that reach the threshold
             B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)nq * fp.cap * 8, st));
-            rc = seed_candidates(samp_keys, nq, k, fp.cap, cand, cand_cnt, st);
-            if (rc) return rc;
-            // 3. all other tiles: score, keep only what beats the sample's k-th best
+            B2R_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * 4, st));
             ScoreOut fo = {};
-            fo.thr_keys = samp_keys;
-            fo.k = k;
+            fo.thr_keys = thr;
             fo.cand = cand;
             fo.cand_cnt = cand_cnt;
             fo.cap = fp.cap;
             fo.n_docs = (uint32_t)ix->n_docs;
             fo.doc_id_base = (uint32_t)ix->doc_id_base;
             if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[0], st));
-            rc = launch_score<SC_OUT_FUSED>(L, (int)q0, nq, SC_TILES_REST, fp.step, fp.n_rest, fo);
+            rc = launch_score<SC_OUT_FUSED>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, fo);
             if (rc) return rc;
             if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[1], st));
-            // 4. top-k of (sample winners + candidates)
+            // 3. exact top-k of the candidates
             rc = topk_keys_rows(cand, nq, fp.cap, fp.cap, fp.cap, 0, k, kout, tk_cand, tk_cand_bytes, st);
             if (rc) return rc;
-            // 5. exact fallback, gated on the device to the queries whose list overflowed
+            // 4. exact fallback, gated on the device to the queries whose list overflowed
             gate.gate = cand_cnt;
             gate.gate_cap = fp.cap;
         }

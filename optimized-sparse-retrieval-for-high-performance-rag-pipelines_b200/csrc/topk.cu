@@ -297,6 +297,65 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
     return topk_keys_rows(dst, n_rows, n2, n2, n2, 0, k, keys_out, wp, left, st, o2);
 }
 
+// ------------------------------------------------------------------------------ k-th of group maxima
+// One CTA per row: radix select (4 passes of 8 bits over the ordered encoding) of the k-th largest of the
+// row's group maxima.  The rows are short (hundreds to a few ten thousand values) and stay in L1/L2.
+__global__ void __launch_bounds__(256)
+kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t row_stride, int k, int lower,
+                     uint64_t *__restrict__ thr_out) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_k;
+    const float *row = maxima + (int64_t)blockIdx.x * row_stride;
+    const int tid = threadIdx.x;
+    uint32_t prefix = 0, mask = 0, kk = (uint32_t)k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < n_groups; i += 256) {
+            const uint32_t o = ord_f32(__ldg(row + i));
+            if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t above = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (above + hist[b] >= kk) break;
+                above += hist[b];
+            }
+            s_prefix = prefix | ((uint32_t)b << shift);
+            s_k = kk - above;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        kk = s_k;
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // prefix = ordered encoding of the k-th largest (if fewer than k values exist the scan above ends in
+        // bin 0 of every pass: prefix <= the encoding of -inf, which also means "no threshold")
+        uint32_t o = prefix;
+        if (o <= 0x007fffffu) {
+            o = 0;
+        } else if (lower) {
+            const float t = unord_f32(o);
+            const float tl = __fsub_rn(__fsub_rn(t, __fmul_rn(fabsf(t), 9.5367431640625e-07f)), 1e-37f);
+            o = ord_f32(tl);
+            if (o <= 0x007fffffu) o = 0;
+        }
+        thr_out[blockIdx.x] = (uint64_t)o << 32;
+    }
+}
+
+int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
+                  uint64_t *thr_out, cudaStream_t st) {
+    if (n_rows == 0) return B2R_OK;
+    kth_of_maxima_kernel<<<(unsigned)n_rows, 256, 0, st>>>(maxima, n_groups, row_stride, k, lower ? 1 : 0, thr_out);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
 // ------------------------------------------------------------------------------------------ decode
 __global__ void decode_keys_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t *__restrict__ idx_out,
                                    float *__restrict__ val_out, const float *__restrict__ scores,
