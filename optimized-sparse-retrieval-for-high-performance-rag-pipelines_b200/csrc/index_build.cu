@@ -22,6 +22,7 @@
 // what scipy's constructor guarantees); a duplicate is reported through the build status flag.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <type_traits>
 
 namespace b2r {
@@ -380,6 +381,16 @@ bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__res
 
 static bool g_bank_schedule = true;
 
+// postings per tile from which a term gets sub-tile offsets (B2R_DENSE_MIN overrides it: tuning experiments only)
+static int dense_min_per_tile() {
+    static const int v = [] {
+        const char *e = getenv("B2R_DENSE_MIN");
+        const int x = e ? atoi(e) : 0;
+        return x >= 1 && x <= 4096 ? x : B2R_DENSE_MIN_PER_TILE;
+    }();
+    return v;
+}
+
 static int tile_shift_of(int tile_docs) {
     int s = 0;
     while ((1 << s) < tile_docs) ++s;
@@ -405,7 +416,7 @@ extern "C" int b2r_index_sizes_for(int64_t nnz, int64_t n_docs, int32_t n_vocab,
     out->post_val_bytes = align_up((size_t)(nnz > 0 ? nnz : 1) * (kind == B2R_KIND_BM25 ? 8 : 4), 256);
     out->blk_ptr_bytes = align_up(entries * 4, 256);
     out->scratch_bytes = 256 + align_up(scan_chunks_for(entries) * 4, 256) + out->post_doc_bytes + out->post_val_bytes;
-    out->n_dense_max = nnz / ((int64_t)B2R_DENSE_MIN_PER_TILE * n_tiles) + 1;
+    out->n_dense_max = nnz / ((int64_t)b2r::dense_min_per_tile() * n_tiles) + 1;
     out->dense_id_bytes = align_up((size_t)n_vocab * 4, 256);
     out->dense_ptr_bytes = align_up((size_t)out->n_dense_max * ((size_t)n_tiles * B2R_SUBTILES + 1) * 4, 256);
     return B2R_OK;
@@ -494,7 +505,7 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
     }
     {
         int32_t *counter = flag + 1;  // scratch[4..8): number of dense terms
-        const uint32_t min_df = (uint32_t)B2R_DENSE_MIN_PER_TILE * (uint32_t)ix->n_tiles;
+        const uint32_t min_df = (uint32_t)dense_min_per_tile() * (uint32_t)ix->n_tiles;
         dense_select_kernel<<<(unsigned)((ix->n_vocab + BLD_THREADS - 1) / BLD_THREADS), BLD_THREADS, 0, st>>>(
             ix->blk_ptr, ix->n_vocab, ix->n_tiles, min_df, ix->n_dense_max, ix->dense_id, counter);
         B2R_LAUNCH_CHECK();
