@@ -117,6 +117,39 @@ int b2r_index_build(const b2r_index *ix, const float *tf, const int32_t *indices
 /* Synchronises the stream and reports malformed input (term id out of range) found by the build. */
 int b2r_index_build_status(const void *scratch, void *stream);
 
+/* ---- On-disk form of a b2r_index (the reference only caches the doc-major CSR as
+ * an .npz, evaluate_rag_pipeline.py:280-312).  One file = this header (4096 bytes) followed by the six device
+ * buffers verbatim, each starting on a 4096-byte boundary, so a shard can be read (or cuFile-DMAed) straight
+ * into HBM with no re-layout.  Little-endian.  The buffers hold shard-local document indices: doc_id_base may
+ * be changed at load time. */
+#define B2R_FILE_MAGIC "B2RIDX01"
+#define B2R_FILE_VERSION 1u
+#define B2R_FILE_ALIGN 4096u
+enum { B2R_SEC_POST_DOC = 0, B2R_SEC_POST_VAL, B2R_SEC_BLK_PTR, B2R_SEC_DENSE_ID, B2R_SEC_DENSE_PTR, B2R_SEC_IDF,
+       B2R_SEC_COUNT };
+typedef struct b2r_file_section {
+    uint64_t offset;   /* from the start of the file, multiple of B2R_FILE_ALIGN */
+    uint64_t bytes;    /* the device buffer size (b2r_index_sizes_for); idf: 4 * n_vocab */
+    uint64_t checksum; /* b2r_checksum64 of the section */
+} b2r_file_section;
+typedef struct b2r_index_file_header {
+    char magic[8];
+    uint32_t version;
+    uint32_t header_bytes; /* B2R_FILE_ALIGN */
+    int64_t n_docs, doc_id_base, nnz;
+    int32_t n_vocab, tile_docs, n_tiles, kind, n_dense_max, subtiles /* B2R_SUBTILES */;
+    double k1, b, avgdl;   /* baked into post_val of a BM25 index */
+    b2r_file_section sections[B2R_SEC_COUNT];
+} b2r_index_file_header;
+/* Host-only helpers (no device access).  b2r_checksum64: order-dependent 64-bit checksum of a byte range
+ * (any length).  b2r_index_file_layout: fills magic/version/sizes/offsets of *hdr from its dimension fields
+ * (n_docs, nnz, n_vocab, tile_docs, kind, n_dense_max; checksums are left 0) and returns the total file size in
+ * *file_bytes.  b2r_index_file_check: validates a header read from a file of file_bytes bytes (magic, version,
+ * dimensions, section sizes and bounds) -- B2R_ERR_DATA with a message when it is not a loadable index. */
+uint64_t b2r_checksum64(const void *data, size_t bytes);
+int b2r_index_file_layout(b2r_index_file_header *hdr, uint64_t *file_bytes);
+int b2r_index_file_check(const b2r_index_file_header *hdr, uint64_t file_bytes);
+
 /* Workspace for b2r_search_batch: *min_bytes lets it run one query at a time, *full_bytes lets it
  * score all n_queries in one pass; anything in between is used as given. */
 int b2r_search_workspace(const b2r_index *ix, int32_t n_queries, int32_t k, size_t *min_bytes,

@@ -49,6 +49,36 @@ class B2RIndexSizes(C.Structure):
     ]
 
 
+class B2RFileSection(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("bytes", C.c_uint64), ("checksum", C.c_uint64)]
+
+
+SEC_NAMES = ("post_doc", "post_val", "blk_ptr", "dense_id", "dense_ptr", "idf")   # B2R_SEC_* order
+FILE_ALIGN = 4096
+
+
+class B2RIndexFileHeader(C.Structure):
+    """struct b2r_index_file_header (include/b200ret.h): first 4096-byte page of an index file."""
+    _fields_ = [
+        ("magic", C.c_char * 8),
+        ("version", C.c_uint32),
+        ("header_bytes", C.c_uint32),
+        ("n_docs", C.c_int64),
+        ("doc_id_base", C.c_int64),
+        ("nnz", C.c_int64),
+        ("n_vocab", C.c_int32),
+        ("tile_docs", C.c_int32),
+        ("n_tiles", C.c_int32),
+        ("kind", C.c_int32),
+        ("n_dense_max", C.c_int32),
+        ("subtiles", C.c_int32),
+        ("k1", C.c_double),
+        ("b", C.c_double),
+        ("avgdl", C.c_double),
+        ("sections", B2RFileSection * 6),
+    ]
+
+
 _P = C.c_void_p
 _I32, _I64, _SZ, _F64 = C.c_int32, C.c_int64, C.c_size_t, C.c_double
 _PIX = C.POINTER(B2RIndex)
@@ -61,6 +91,9 @@ SIGNATURES = {
     "b2r_index_sizes_for": (C.c_int, [_I64, _I64, _I32, _I32, _I32, C.POINTER(B2RIndexSizes)]),
     "b2r_index_build": (C.c_int, [_PIX, _P, _P, _P, _P, _F64, _F64, _F64, _P, _SZ, _P]),
     "b2r_index_build_status": (C.c_int, [_P, _P]),
+    "b2r_checksum64": (C.c_uint64, [_P, _SZ]),
+    "b2r_index_file_layout": (C.c_int, [C.POINTER(B2RIndexFileHeader), C.POINTER(C.c_uint64)]),
+    "b2r_index_file_check": (C.c_int, [C.POINTER(B2RIndexFileHeader), C.c_uint64]),
     "b2r_search_workspace": (C.c_int, [_PIX, _I32, _I32, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "b2r_search_batch": (C.c_int, [_PIX, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "b2r_set_fused_selection": (None, [C.c_int]),

@@ -17,6 +17,8 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b2r {
 
 constexpr int I8_THREADS = 256;
@@ -241,6 +243,9 @@ struct MmOut {
     int32_t *cand_cnt;   // [n_q]
     int32_t cap;
     uint32_t doc_id_base;
+    // B2R_INT8_DIAG (measurement only, results are garbage): 1 = the epilogue releases every accumulator
+    // unread, 2 = additionally no MMA is issued (pure TMA ring rate)
+    int32_t diag;
 };
 
 template <int OUT>
@@ -366,7 +371,7 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
                     for (int ks = 0; ks < MM_KC / MM_UK; ++ks) {
                         const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * MM_CHUNK_BYTES + ks * MM_UK));
                         const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * MM_CHUNK_BYTES + ks * MM_UK));
-                        umma_s8(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                        if (o.diag < 2) umma_s8(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
                     }
                     // frees the smem slot (in every CTA of the cluster) when these MMAs are done
                     if (csize == 1) umma_commit(&bars.empty[stage]);
@@ -405,7 +410,11 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
             const bool ds_sane = fabsf(dsf) >= 1e-15f && fabsf(dsf) <= 1e15f;
             mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {
+            if (o.diag >= 1) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.tempty[acc]);
+            } else {
                 const int cc = 1;  // (one 32-column group per warp: its only load is also its last)
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * MM_N + c0);
@@ -562,8 +571,16 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
                            cudaStream_t st, int *gy_out = nullptr) {
     if (n_q == 0 || n_logical == 0) return B2R_OK;
     const int n_kc = dim / MM_KC;
-    int n_stages = (200 * 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
+    // ring depth: everything the 227 KB of shared memory leave next to the resident query tile (static arrays
+    // and the 1 KB alignment slack come off first); B2R_INT8_STAGES overrides it (tuning experiments only)
+    int n_stages = (232448 - 4096 - 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
     if (n_stages > MM_MAX_STAGES) n_stages = MM_MAX_STAGES;
+    static const int stage_cap = [] {
+        const char *e = getenv("B2R_INT8_STAGES");
+        const int v = e ? atoi(e) : 0;
+        return v >= 2 && v <= MM_MAX_STAGES ? v : MM_MAX_STAGES;
+    }();
+    if (n_stages > stage_cap) n_stages = stage_cap;
     const size_t smem = (size_t)(n_kc + n_stages) * MM_CHUNK_BYTES + 1024;
     CUtensorMap map_d, map_q;
     int rc = make_rowmajor_i8_map(&map_d, d8, n_docs, dim);
@@ -601,8 +618,14 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
     if (gy > n_logical) gy = n_logical;
     cfg.gridDim = dim3((unsigned)gx, (unsigned)gy);
     if (gy_out) *gy_out = (int)gy;
+    static const int diag = [] {
+        const char *e = getenv("B2R_INT8_DIAG");
+        return e ? atoi(e) : 0;
+    }();
+    MmOut od = o;
+    od.diag = diag;
     B2R_CUDA(cudaLaunchKernelEx(&cfg, int8_mma_kernel<OUT>, map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, tile_mode,
-                                tile_step, n_logical, o));
+                                tile_step, n_logical, od));
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }

@@ -185,6 +185,92 @@ class TermMajorIndex:
         del tf_d, ind_d, ptr_d, dl_d, scratch
         return self
 
+    # ------------------------------------------------------------------ on-disk form
+    _IO_CHUNK = 64 << 20
+
+    def save(self, path) -> int:
+        """Write the HBM layout verbatim to `path` (format: include/b200ret.h, b2r_index_file_header): a 4096-byte
+        header, then post_doc / post_val / blk_ptr / dense_id / dense_ptr / idf, each 4096-aligned and
+        checksummed.  The reference can only cache the doc-major CSR (.npz, evaluate_rag_pipeline.py:280-312)
+        and rebuilds everything else on load; this file goes back to HBM with no re-layout.  Returns the file size."""
+        hdr = _abi.B2RIndexFileHeader()
+        d = self._desc
+        hdr.n_docs, hdr.doc_id_base, hdr.nnz = d.n_docs, d.doc_id_base, d.nnz
+        hdr.n_vocab, hdr.tile_docs, hdr.kind, hdr.n_dense_max = d.n_vocab, d.tile_docs, d.kind, d.n_dense_max
+        hdr.k1, hdr.b, hdr.avgdl = self.k1, self.b, self.avgdl
+        total = C.c_uint64(0)
+        _abi.check(_abi.lib.b2r_index_file_layout(C.byref(hdr), C.byref(total)), "index file layout")
+        torch.cuda.synchronize(self.device)
+        stage = torch.empty(self._IO_CHUNK, dtype=torch.uint8).pin_memory()
+        with open(path, "wb") as f:
+            f.truncate(total.value)
+            for i, name in enumerate(_abi.SEC_NAMES):
+                sec = hdr.sections[i]
+                buf = self._bufs[name].view(torch.uint8).reshape(-1)
+                if buf.numel() != sec.bytes:
+                    raise _abi.B2RError(f"index file: buffer {name} has {buf.numel()} bytes, layout says {sec.bytes}")
+                f.seek(sec.offset)
+                # chained checksum: every chunk is folded into the running value of the section
+                acc = 0
+                for o in range(0, int(sec.bytes), self._IO_CHUNK):
+                    n = min(self._IO_CHUNK, int(sec.bytes) - o)
+                    stage[:n].copy_(buf[o:o + n])
+                    acc = _chain_checksum(acc, stage, n)
+                    f.write(memoryview(stage.numpy())[:n])
+                sec.checksum = acc
+            f.seek(0)
+            f.write(bytes(hdr))
+        return int(total.value)
+
+    @classmethod
+    def load(cls, path, *, device=None, doc_id_base: Optional[int] = None, verify: bool = True) -> "TermMajorIndex":
+        """Read an index written by save() straight into HBM (no CSR, no build kernels).  `doc_id_base` re-bases
+        the shard (the buffers hold shard-local document indices); `verify` checks every section's checksum."""
+        import os
+        self = cls()
+        dev = self.device = _cuda_device(device)
+        size = os.path.getsize(path)
+        hdr = _abi.B2RIndexFileHeader()
+        with open(path, "rb") as f:
+            raw = f.read(C.sizeof(hdr))
+            if len(raw) < C.sizeof(hdr):
+                raise ValueError(f"{path}: not a b200ret index file (too short)")
+            C.memmove(C.byref(hdr), raw, C.sizeof(hdr))
+            _abi.check(_abi.lib.b2r_index_file_check(C.byref(hdr), size), f"{path}")
+            stage = torch.empty(cls._IO_CHUNK, dtype=torch.uint8).pin_memory()
+            for i, name in enumerate(_abi.SEC_NAMES):
+                sec = hdr.sections[i]
+                buf = torch.empty(int(sec.bytes), dtype=torch.uint8, device=dev)
+                f.seek(sec.offset)
+                acc = 0
+                for o in range(0, int(sec.bytes), cls._IO_CHUNK):
+                    n = min(cls._IO_CHUNK, int(sec.bytes) - o)
+                    got = f.readinto(memoryview(stage.numpy())[:n])
+                    if got != n:
+                        raise ValueError(f"{path}: section {name} is truncated")
+                    if verify:
+                        acc = _chain_checksum(acc, stage, n)
+                    buf[o:o + n].copy_(stage[:n])
+                    torch.cuda.current_stream(dev).synchronize()      # the staging buffer is reused
+                if verify and acc != sec.checksum:
+                    raise ValueError(f"{path}: checksum mismatch in section {name} (file is corrupt)")
+                self._bufs[name] = buf
+        self.kind = "bm25" if hdr.kind == _abi.KIND_BM25 else "impact"
+        self.n_docs, self.n_vocab, self.nnz = int(hdr.n_docs), int(hdr.n_vocab), int(hdr.nnz)
+        self.tile_docs, self.n_tiles = int(hdr.tile_docs), int(hdr.n_tiles)
+        self.doc_id_base = int(hdr.doc_id_base if doc_id_base is None else doc_id_base)
+        if self.doc_id_base < 0 or self.doc_id_base + self.n_docs >= 0xFFFFFFFF:
+            raise ValueError("doc_id_base out of range")
+        self.k1, self.b, self.avgdl = float(hdr.k1), float(hdr.b), float(hdr.avgdl)
+        self._bufs["idf"] = self._bufs["idf"].view(torch.float32)
+        self.idf_host = self._bufs["idf"].cpu().numpy()
+        d, b_ = self._desc, self._bufs
+        d.n_docs, d.doc_id_base, d.nnz = self.n_docs, self.doc_id_base, self.nnz
+        d.n_vocab, d.tile_docs, d.n_tiles, d.kind = self.n_vocab, self.tile_docs, self.n_tiles, int(hdr.kind)
+        d.post_doc, d.post_val, d.blk_ptr = b_["post_doc"].data_ptr(), b_["post_val"].data_ptr(), b_["blk_ptr"].data_ptr()
+        d.dense_id, d.dense_ptr, d.n_dense_max = b_["dense_id"].data_ptr(), b_["dense_ptr"].data_ptr(), int(hdr.n_dense_max)
+        return self
+
     # ------------------------------------------------------------------ properties
     @property
     def padded_docs(self) -> int:
@@ -293,6 +379,13 @@ class TermMajorIndex:
     def postings_touched(self, q_ptr: np.ndarray, q_terms: np.ndarray, df: np.ndarray) -> int:
         """P = sum over queries and their terms of df[t] on this shard."""
         return int(np.asarray(df, dtype=np.int64)[np.asarray(q_terms, dtype=np.int64)].sum())
+
+
+def _chain_checksum(acc: int, stage: torch.Tensor, n: int) -> int:
+    """Running checksum of a section written/read in chunks: fold the chunk's b2r_checksum64 into `acc`."""
+    c = int(_abi.lib.b2r_checksum64(stage.data_ptr(), n))
+    word = np.array([acc, c], dtype=np.uint64)
+    return int(_abi.lib.b2r_checksum64(word.ctypes.data, 16))
 
 
 def _to_numpy(x) -> np.ndarray:

@@ -144,6 +144,52 @@ class RetrievalService:
             self._gpu_params = params
         return self._gpu_index
 
+    # ------------------------------------------------------------------ save / load
+    def save_bm25_index(self, path: Union[str, Path]) -> None:
+        """Persist the built index: `<path>` holds the term-major HBM layout (TermMajorIndex.save), and
+        `<path>.meta.npz` the host attributes under the keys of the reference's own index cache
+        (evaluate_rag_pipeline.py:280-293: tf_data, tf_indices, tf_indptr, tf_shape, doc_lengths, idf,
+        vocabulary, doc_ids, avgdl) plus k1, b -- so a cache written by the reference loads here too."""
+        if self.corpus_tf is None:
+            raise ValueError("BM25 index not built. Call build_bm25_index() first.")
+        path = Path(path)
+        self._sync_gpu_index().save(path)
+        tf = self.corpus_tf
+        with open(str(path) + ".meta.npz", "wb") as f:
+            np.savez_compressed(
+                f, tf_data=tf.data, tf_indices=tf.indices, tf_indptr=tf.indptr, tf_shape=np.asarray(tf.shape),
+                doc_lengths=self.doc_lengths, idf=self.idf_weights,
+                vocabulary=np.asarray(sorted(self.vocabulary, key=self.vocabulary.get), dtype=object),
+                doc_ids=np.asarray(self.doc_ids, dtype=object), avgdl=self.avgdl, k1=self.k1, b=self.b)
+
+    def load_bm25_index(self, path: Union[str, Path], verify: bool = True) -> None:
+        """Inverse of save_bm25_index.  The HBM layout is read back as is (no build kernels) when `<path>` exists
+        and was built with the same k1 / b / avgdl; otherwise (e.g. a cache file of the reference: only the
+        .npz) it is rebuilt from the CSR."""
+        path = Path(path)
+        meta_path = Path(str(path) + ".meta.npz") if not str(path).endswith(".npz") else path
+        cached = np.load(meta_path, allow_pickle=True)
+        shape = tuple(int(x) for x in cached["tf_shape"])
+        self.corpus_tf = csr_matrix((cached["tf_data"], cached["tf_indices"], cached["tf_indptr"]), shape=shape)
+        self.doc_lengths = np.asarray(cached["doc_lengths"], dtype=np.float32)
+        self.idf_weights = np.asarray(cached["idf"], dtype=np.float32)
+        self.vocabulary = {str(t): i for i, t in enumerate(cached["vocabulary"])}
+        self.doc_ids = [str(d) for d in cached["doc_ids"]]
+        self.avgdl = float(cached["avgdl"])
+        if "k1" in cached:
+            self.k1, self.b = float(cached["k1"]), float(cached["b"])
+        with self.cache_lock:
+            self.query_cache.clear()
+        self._gpu_index, self._gpu_params = None, None
+        if meta_path != path and path.exists():
+            ix = TermMajorIndex.load(path, verify=verify)
+            params = (float(self.k1), float(self.b), float(self.avgdl))
+            if (ix.kind == "bm25" and ix.n_docs == shape[0] and ix.n_vocab == shape[1] and
+                    (ix.k1, ix.b, ix.avgdl) == params and np.array_equal(ix.idf_host, self.idf_weights)):
+                self.tile_docs = ix.tile_docs
+                self._gpu_index, self._gpu_params = ix, params
+        self._sync_gpu_index()
+
     # ------------------------------------------------------------------ search
     def search_bm25(self, queries: Dict[str, str], top_k: int = 10) -> Dict[str, Dict[str, float]]:
         """retrieval.py:203-296, batched.  All queries that miss the cache are scored in one GPU pass."""

@@ -58,6 +58,58 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in src, f
 
 
+def test_index_file_header_layout_and_validation():
+    """Host-only part of the on-disk index format (include/b200ret.h): layout, checksum, every rejection."""
+    import ctypes as C
+    import b200ret
+    from b200ret import _abi
+    lib = _abi.lib
+    assert C.sizeof(_abi.B2RIndexFileHeader) <= _abi.FILE_ALIGN
+
+    def fresh():
+        h = _abi.B2RIndexFileHeader()
+        h.n_docs, h.nnz, h.n_vocab, h.tile_docs, h.kind, h.n_dense_max = 10_000, 123_456, 777, 1024, 0, 5
+        h.k1, h.b, h.avgdl = 1.2, 0.75, 12.5
+        total = C.c_uint64(0)
+        assert lib.b2r_index_file_layout(C.byref(h), C.byref(total)) == 0
+        return h, total.value
+
+    h, total = fresh()
+    assert h.magic == b"B2RIDX01" and h.version == 1 and h.header_bytes == 4096 and h.n_tiles == 10 and h.subtiles == 8
+    sizes = _abi.B2RIndexSizes()
+    assert lib.b2r_index_sizes_for(123_456, 10_000, 777, 1024, 0, C.byref(sizes)) == 0
+    want = [sizes.post_doc_bytes, sizes.post_val_bytes, sizes.blk_ptr_bytes, sizes.dense_id_bytes, None, 777 * 4]
+    end = 4096
+    for i, sec in enumerate(h.sections):
+        assert sec.offset % 4096 == 0 and sec.offset >= end and (want[i] is None or sec.bytes == want[i])
+        end = sec.offset + sec.bytes
+    assert end <= total and total % 4096 == 0
+    assert lib.b2r_index_file_check(C.byref(h), total) == 0
+
+    def rejected(mutate, size=None):
+        g, tot = fresh()
+        mutate(g)
+        rc = lib.b2r_index_file_check(C.byref(g), tot if size is None else size)
+        return rc == -5 and len(lib.b2r_last_error()) > 0
+
+    assert rejected(lambda g: setattr(g, "magic", b"NOTANIDX"))
+    assert rejected(lambda g: setattr(g, "version", 2))
+    assert rejected(lambda g: setattr(g, "n_tiles", 11))
+    assert rejected(lambda g: setattr(g, "tile_docs", 1000))                 # not a power of two
+    assert rejected(lambda g: setattr(g.sections[1], "bytes", g.sections[1].bytes - 8))
+    assert rejected(lambda g: setattr(g.sections[2], "offset", g.sections[2].offset + 16))
+    assert rejected(lambda g: None, size=total - 4096)                       # truncated file
+    assert rejected(lambda g: setattr(g, "doc_id_base", 2 ** 32))
+
+    a = np.arange(4099, dtype=np.uint8)
+    c0 = lib.b2r_checksum64(a.ctypes.data, a.size)
+    assert c0 == lib.b2r_checksum64(a.copy().ctypes.data, a.size)
+    assert c0 != lib.b2r_checksum64(a.ctypes.data, a.size - 1)
+    b = a.copy(); b[4000] ^= 1
+    assert c0 != lib.b2r_checksum64(b.ctypes.data, b.size)
+    assert lib.b2r_checksum64(None, 0) == lib.b2r_checksum64(a.ctypes.data, 0)
+
+
 def test_pack_queries_matches_dense_query_tf():
     import b200ret
     ptr, terms, w = b200ret.pack_queries([([5, 2, 5, 9], [1.0, 2.0, 3.0, 0.0]), ([], []), ([7], [-1.0]), ([1, 0], [4, 5])])

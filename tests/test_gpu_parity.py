@@ -455,6 +455,73 @@ def test_service_text_api_vs_reference(b2r, golden_dir, tmp_path):
         assert svc.get_stats()["query_cache_size"] == 0
 
 
+def test_index_file_roundtrip_and_corruption(b2r, tmp_path):
+    """save() -> load(): every device buffer comes back bit for bit, searches agree, a re-based shard keeps global
+    ids, and a flipped byte / truncated file / foreign file is refused."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab, k = 20_000 + 7, 3000, 10
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 40, seed=51)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    q_ptr, q_terms, q_w = S.zipf_queries(40, n_vocab, seed=52)
+    for kind in ("bm25", "impact"):
+        ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl,
+                                         tile_docs=512, kind=kind, k1=1.4, b=0.6, doc_id_base=5000)
+        path = tmp_path / f"shard_{kind}.b2r"
+        size = ix.save(path)
+        assert size == os.path.getsize(path) and size % 4096 == 0
+        ld = b2r.TermMajorIndex.load(path)
+        assert (ld.kind, ld.n_docs, ld.n_vocab, ld.nnz, ld.tile_docs, ld.n_tiles, ld.doc_id_base) == \
+               (ix.kind, ix.n_docs, ix.n_vocab, ix.nnz, ix.tile_docs, ix.n_tiles, 5000)
+        assert (ld.k1, ld.b, ld.avgdl) == (1.4, 0.6, ix.avgdl)
+        for name in ("post_doc", "post_val", "blk_ptr", "dense_id", "dense_ptr", "idf"):
+            assert torch.equal(ix._bufs[name].view(torch.uint8).reshape(-1), ld._bufs[name].view(torch.uint8).reshape(-1)), name
+        i0, v0 = ix.search(q_ptr, q_terms, q_w, k)
+        i1, v1 = ld.search(q_ptr, q_terms, q_w, k)
+        assert torch.equal(i0, i1) and torch.equal(v0, v1)
+        assert np.array_equal(ld.search_host(q_ptr, q_terms, q_w, k)[0], i0.cpu().numpy())
+        rb = b2r.TermMajorIndex.load(path, doc_id_base=0)
+        i2, v2 = rb.search(q_ptr, q_terms, q_w, k)
+        assert torch.equal(i2 + 5000, i0) and torch.equal(v2, v0)
+    raw = bytearray(path.read_bytes())
+    bad = tmp_path / "flipped.b2r"
+    raw[4096 + 100] ^= 0x40
+    bad.write_bytes(raw)
+    with pytest.raises(ValueError, match="checksum"):
+        b2r.TermMajorIndex.load(bad)
+    assert b2r.TermMajorIndex.load(bad, verify=False).n_docs == n_docs          # (checks can be skipped explicitly)
+    (tmp_path / "short.b2r").write_bytes(bytes(raw[:len(raw) // 2]))
+    with pytest.raises(ValueError, match="exceeds the file"):
+        b2r.TermMajorIndex.load(tmp_path / "short.b2r")
+    (tmp_path / "foreign.b2r").write_bytes(b"PK\x03\x04" + bytes(8000))
+    with pytest.raises(ValueError, match="magic"):
+        b2r.TermMajorIndex.load(tmp_path / "foreign.b2r")
+
+
+def test_service_save_load_and_reference_cache_file(b2r, golden_dir, tmp_path):
+    """RetrievalService.save_bm25_index / load_bm25_index: the loaded service answers like the built one without
+    running the build kernels; a cache file in the reference's own .npz layout (no .b2r next to it) also loads."""
+    g = json.load(open(os.path.join(golden_dir, "service_text.json")))
+    store = tmp_path / "docs.idx"
+    b2r.MemoryIndex(store, create=True).close()
+    svc = b2r.RetrievalService(store)
+    svc.build_bm25_index(g["corpus"])
+    want = svc.search_bm25(g["queries"], top_k=10)
+    svc.save_bm25_index(tmp_path / "bm25.b2r")
+    launches = b2r._abi.lib.b2r_launch_count()
+    svc2 = b2r.RetrievalService(store)
+    svc2.load_bm25_index(tmp_path / "bm25.b2r")
+    assert b2r._abi.lib.b2r_launch_count() == launches                  # no build kernel ran
+    assert svc2.search_bm25(g["queries"], top_k=10) == want
+    assert svc2.vocabulary == svc.vocabulary and svc2.doc_ids == svc.doc_ids and svc2.avgdl == svc.avgdl
+    tf = svc.corpus_tf                                                  # reference layout: evaluate_rag_pipeline.py:280-293
+    np.savez_compressed(tmp_path / "ref_cache.npz", tf_data=tf.data, tf_indices=tf.indices, tf_indptr=tf.indptr,
+                        tf_shape=tf.shape, doc_lengths=svc.doc_lengths, idf=svc.idf_weights,
+                        vocabulary=list(svc.vocabulary.keys()), doc_ids=svc.doc_ids, avgdl=svc.avgdl)
+    svc3 = b2r.RetrievalService(store)
+    svc3.load_bm25_index(tmp_path / "ref_cache.npz")
+    assert svc3.search_bm25(g["queries"], top_k=10) == want
+
+
 def test_registry_plugin_shape(b2r, golden_dir):
     with open(os.path.join(golden_dir, "service_text.json")) as f:
         g = json.load(f)

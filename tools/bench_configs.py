@@ -86,7 +86,7 @@ def zipf_csr_torch(n_docs, n_vocab, mean_len, seed, dev, distinct_per_doc=None, 
 
 def run_int8(args):
     dev = torch.device("cuda")
-    n, dim, k = args.docs, 768, 100
+    n, dim, k = args.docs, 768, args.k
     g = torch.Generator(device=dev); g.manual_seed(42)
     d8 = torch.randint(-127, 128, (n, dim), device=dev, dtype=torch.int8, generator=g)
     ds = torch.rand(n, device=dev, generator=g) + 0.01
@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--docs", type=int, default=None)
     ap.add_argument("--queries", type=int, nargs="+", default=[1, 64, 1024])
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--k", type=int, default=100, help="int8: top-k")
     ap.add_argument("--fused-modes", type=int, nargs="*", default=None,
                     help="int8: sweep b2r_set_int8_fused (0 plain, 1 default gate, 2 fused for every batch size)")
     ap.add_argument("--clusters", type=int, nargs="*", default=None,
