@@ -227,6 +227,21 @@ int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t 
                        uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* Hybrid sparse -> dense rerank on candidates only (the reference names a "hybrid"
+ * retriever in configs/ms_marco_paper_results.yaml:108-124 but has no implementation).  cand_idx i64[n_q, k_in]
+ * holds global document indices (e.g. idx_out of b2r_search_batch; < 0 or outside this shard = no candidate),
+ * cand_sparse f32[n_q, k_in] their sparse scores or NULL.  For every pair the INT8 similarity
+ * f32((f64(dot) * f64(q_scale[q])) * f64(d_scale[doc])) is evaluated on the candidate's vector
+ * (retriever_registry.py:90-117 restricted to the candidates), then
+ *   score = cand_sparse ? f32(f64(sparse_weight) * f64(sparse) + f64(dense_weight) * f64(dense)) : dense
+ * and the k_out best per query are returned (score descending, document index ascending; -1 / -inf padding).
+ * dense_out: optional f32[n_q, k_in] dense similarities (-inf for "no candidate"). */
+int b2r_int8_rerank_workspace(int32_t n_q, int32_t k_in, int32_t k_out, size_t *bytes);
+int b2r_int8_rerank(const int64_t *cand_idx, const float *cand_sparse, int32_t n_q, int32_t k_in, const int8_t *q8,
+                    const float *q_scale, const int8_t *d8, const float *d_scale, int64_t n_docs, int32_t dim,
+                    int64_t doc_id_base, float sparse_weight, float dense_weight, int32_t k_out, float *dense_out,
+                    int64_t *idx_out, float *val_out, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

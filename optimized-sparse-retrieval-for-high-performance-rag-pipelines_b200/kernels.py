@@ -51,7 +51,7 @@ def set_int8_fused(mode) -> None:
 
 __all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_bank_schedule", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
-           "int8_scan_topk"]
+           "int8_scan_topk", "int8_rerank", "hybrid_search"]
 
 # key -> (index, the source arrays: holding them keeps their addresses from being reused)
 _INDEX_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -195,6 +195,57 @@ def int8_scan_topk(queries_int8, corpus_int8, query_scales, corpus_scales, k: in
                                            int(doc_id_base), keys.data_ptr(), idx.data_ptr(), val.data_ptr(),
                                            ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "int8 scan")
     return idx, val, keys
+
+
+def int8_rerank(cand_idx, cand_sparse, queries_int8, query_scales, corpus_int8, corpus_scales, k_out: int, *,
+                sparse_weight: float = 0.3, dense_weight: float = 0.7, doc_id_base: int = 0, return_dense: bool = False):
+    """Hybrid sparse -> dense rerank on candidates only (the reference only names this retriever:
+    configs/ms_marco_paper_results.yaml:108-124, sparse_weight 0.3 / dense_weight 0.7).
+
+    cand_idx i64[Q, k_in] are global document indices (e.g. TermMajorIndex.search output; -1 = none), cand_sparse
+    their sparse scores f32[Q, k_in] or None (pure dense rerank).  For every pair the INT8 similarity of
+    quantized_dot_product_batch is evaluated on the candidate's vector only; score = f32(f64(ws) * f64(sparse)
+    + f64(wd) * f64(dense)).  Returns CUDA tensors (idx i64[Q, k_out], score f32[Q, k_out][, dense f32[Q, k_in]])."""
+    dev = _cuda_device(corpus_int8.device if isinstance(corpus_int8, torch.Tensor) and corpus_int8.is_cuda else None)
+    ci = _to_device(cand_idx, torch.int64, dev)
+    cs = _to_device(cand_sparse, torch.float32, dev) if cand_sparse is not None else None
+    q8 = _to_device(queries_int8, torch.int8, dev)
+    d8 = _to_device(corpus_int8, torch.int8, dev)
+    qs = _to_device(query_scales, torch.float32, dev).reshape(-1)
+    ds = _to_device(corpus_scales, torch.float32, dev).reshape(-1)
+    if ci.dim() != 2 or q8.dim() != 2 or d8.dim() != 2 or q8.shape[1] != d8.shape[1] or ci.shape[0] != q8.shape[0]:
+        raise ValueError("cand_idx [Q, k_in], queries_int8 [Q, dim] and corpus_int8 [N, dim] do not fit together")
+    if cs is not None and tuple(cs.shape) != tuple(ci.shape):
+        raise ValueError("cand_sparse must have the shape of cand_idx")
+    if qs.numel() != q8.shape[0] or ds.numel() != d8.shape[0]:
+        raise ValueError("one scale per query row and per corpus row is required")
+    nq, k_in = int(ci.shape[0]), int(ci.shape[1])
+    k_out = min(int(k_out), k_in)
+    if k_out < 1:
+        raise ValueError("k_out must be >= 1")
+    nbytes = C.c_size_t(0)
+    _abi.check(_abi.lib.b2r_int8_rerank_workspace(nq, k_in, k_out, C.byref(nbytes)), "rerank workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    idx = torch.empty((nq, k_out), dtype=torch.int64, device=dev)
+    val = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+    dense = torch.empty((nq, k_in), dtype=torch.float32, device=dev) if return_dense else None
+    _abi.check(_abi.lib.b2r_int8_rerank(ci.data_ptr(), cs.data_ptr() if cs is not None else None, nq, k_in,
+                                        q8.data_ptr(), qs.data_ptr(), d8.data_ptr(), ds.data_ptr(), int(d8.shape[0]),
+                                        int(d8.shape[1]), int(doc_id_base), float(sparse_weight), float(dense_weight),
+                                        k_out, dense.data_ptr() if dense is not None else None, idx.data_ptr(),
+                                        val.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "int8 rerank")
+    return (idx, val, dense) if return_dense else (idx, val)
+
+
+def hybrid_search(index: TermMajorIndex, q_ptr, q_terms, q_weights, queries_int8, query_scales, corpus_int8,
+                  corpus_scales, k_candidates: int, k_out: int, *, sparse_weight: float = 0.3,
+                  dense_weight: float = 0.7):
+    """BM25 (or impact) top-k_candidates on the term-major index, then int8_rerank on those candidates: the
+    two-stage "hybrid" retriever of the reference's MS MARCO config, every stage on the GPU.  The corpus rows of
+    `corpus_int8` are the documents of `index` (same shard, same order)."""
+    idx, val = index.search(q_ptr, q_terms, q_weights, k_candidates)
+    return int8_rerank(idx, val, queries_int8, query_scales, corpus_int8, corpus_scales, k_out,
+                       sparse_weight=sparse_weight, dense_weight=dense_weight, doc_id_base=index.doc_id_base)
 
 
 # ----------------------------------------------------------------------------- README aliases

@@ -214,3 +214,41 @@ def search_bm25_text(ix, queries: Dict[str, str], top_k: int = 10, k1: float = 1
         idx, val = topk_canonical(s, top_k)
         out[qid] = {ix["doc_ids"][i]: float(v) for i, v in zip(idx, val) if v > 0}
     return out
+
+
+def hybrid_rerank(cand_idx, cand_sparse, q8, q_scales, d8, d_scales, sparse_weight, dense_weight, k_out,
+                  doc_id_base=0):
+    """Candidate-only INT8 rerank + linear score fusion.  The reference NAMES this retriever
+    (rag_system/configs/ms_marco_paper_results.yaml:108-124: type "hybrid", sparse_weight 0.3, dense_weight 0.7)
+    but ships no implementation, so there is nothing to pin it to -- parity unpinned for the fusion rule; the
+    dense part is quantized_dot_product_batch (retriever_registry.py:90-117, pinned by tests/golden/int8.npz)
+    restricted to the candidates.  Semantics checked against the CUDA path:
+        dense  = f32((f64(int dot) * f64(qs)) * f64(ds))
+        score  = f32(f64(f32 ws) * f64(sparse) + f64(f32 wd) * f64(dense))      (dense alone if cand_sparse is None)
+    rank by score descending, document index ascending; candidates < 0 or outside the shard are skipped.
+    Returns (idx i64[Q, k_out] padded with -1, score f32[Q, k_out] padded with -inf, dense f32[Q, k_in])."""
+    cand_idx = np.asarray(cand_idx, np.int64)
+    nq, k_in = cand_idx.shape
+    ws, wd = np.float64(np.float32(sparse_weight)), np.float64(np.float32(dense_weight))
+    out_i = np.full((nq, k_out), -1, np.int64)
+    out_v = np.full((nq, k_out), -np.inf, np.float32)
+    dense_all = np.full((nq, k_in), -np.inf, np.float32)
+    for q in range(nq):
+        loc = cand_idx[q] - doc_id_base
+        ok = (cand_idx[q] >= 0) & (loc >= 0) & (loc < len(d8))
+        if not ok.any():
+            continue
+        rows = loc[ok]
+        dots = d8[rows].astype(np.int64) @ q8[q].astype(np.int64)
+        dense = ((dots.astype(np.float64) * np.float64(q_scales[q])) * d_scales[rows].astype(np.float64)).astype(np.float32)
+        dense_all[q, ok] = dense
+        if cand_sparse is None:
+            score = dense
+        else:
+            score = (ws * np.asarray(cand_sparse, np.float32)[q, ok].astype(np.float64)
+                     + wd * dense.astype(np.float64)).astype(np.float32)
+        ids = cand_idx[q, ok]
+        order = np.lexsort((ids, -np.where(score == 0, np.float32(0), score)))[:k_out]
+        out_i[q, :len(order)] = ids[order]
+        out_v[q, :len(order)] = np.where(score[order] == 0, np.float32(0), score[order])
+    return out_i, out_v, dense_all

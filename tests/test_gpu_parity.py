@@ -174,6 +174,60 @@ def test_int8_fused_scan_equals_plain_and_survives_overflow(b2r, k):
             assert np.array_equal(_bits(fv[q].cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
 
 
+@pytest.mark.parametrize("dim", [768, 100])
+def test_int8_rerank_on_candidates_vs_oracle(b2r, dim):
+    """f3: candidate-only INT8 rerank + score fusion against the numpy restatement (bit-exact scores, exact ids),
+    with missing candidates (-1), candidates of another shard, duplicates of scores (ties -> lower doc id first),
+    pure dense rerank (no sparse scores) and the dense similarities equal to quantized_dot_product_batch."""
+    rng = np.random.default_rng(61 + dim)
+    nq, n, k_in, k_out, base = 37, 5000, 100, 10, 20_000
+    q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+    d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
+    d8[100:140] = d8[100]                                             # identical vectors: score ties
+    qs = (rng.random(nq).astype(np.float32) + 0.01) / 127
+    ds = rng.random(n).astype(np.float32) + 0.01
+    ds[100:140] = ds[100]
+    cand = np.stack([rng.choice(n, k_in, replace=False) for _ in range(nq)]).astype(np.int64) + base
+    cand[0, :40] = np.arange(100, 140) + base                         # the tied block, all with one sparse score
+    cand[1, 5:9] = -1
+    cand[2, 50:] = -1
+    cand[3, 10] = base + n + 5                                        # beyond this shard
+    cand[3, 11] = base - 1
+    sparse = (rng.random((nq, k_in)).astype(np.float32) * 20).astype(np.float32)
+    sparse[0, :40] = 3.25
+    for sp, (w_s, w_d) in ((sparse, (0.3, 0.7)), (sparse, (1.0, 0.0)), (None, (0.3, 0.7))):
+        gi, gv, gd = b2r.int8_rerank(cand, sp, q8, qs, d8, ds, k_out, sparse_weight=w_s, dense_weight=w_d,
+                                     doc_id_base=base, return_dense=True)
+        wi, wv, wd = np_oracle.hybrid_rerank(cand, sp, q8, qs, d8, ds, w_s, w_d, k_out, doc_id_base=base)
+        assert np.array_equal(gi.cpu().numpy(), wi)
+        assert np.array_equal(_bits(gv.cpu().numpy()), _bits(wv))
+        assert np.array_equal(_bits(gd.cpu().numpy()), _bits(wd))
+    full = b2r.quantized_dot_product_batch(q8, d8, qs, ds)            # the reference kernel's drop-in, whole corpus
+    ok = (cand >= base) & (cand < base + n)
+    for q in (0, 1, 3, nq - 1):
+        assert np.array_equal(_bits(gd.cpu().numpy()[q][ok[q]]), _bits(full[q][cand[q][ok[q]] - base]))
+
+
+def test_hybrid_search_two_stage(b2r):
+    """BM25 top-100 -> INT8 rerank -> top-10 through hybrid_search equals oracle BM25 top-100 + oracle rerank."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab, dim = 30_000, 3000, 256
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 40, seed=71)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    q_ptr, q_terms, q_w = S.zipf_queries(24, n_vocab, seed=72)
+    rng = np.random.default_rng(73)
+    x = rng.standard_normal((n_docs, dim)).astype(np.float32)
+    d8, ds = np_oracle.quantize_rows(x)
+    xq = rng.standard_normal((24, dim)).astype(np.float32)
+    q8, qs = np_oracle.quantize_rows(xq); qs = (qs / 127).astype(np.float32)
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=1024)
+    gi, gv = b2r.hybrid_search(ix, q_ptr, q_terms, q_w, q8, qs, d8, ds, 100, 10, sparse_weight=0.3, dense_weight=0.7)
+    ci, cv = _oracle_topk((data, indices, indptr, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, 100)
+    cv = np.where(cv == 0, np.float32(0), cv)
+    wi, wv, _ = np_oracle.hybrid_rerank(ci, cv, q8, qs, d8, ds, 0.3, 0.7, 10)
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(_bits(gv.cpu().numpy()), _bits(wv))
+
+
 # ----------------------------------------------------------------------------------- golden + edge: K2
 def test_topk_reference_cases(b2r, golden_dir):
     z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
