@@ -38,6 +38,8 @@ WORKLOADS = {
     "c3": (8_800_000, 100_000, 60.0, 1024, 100,
            "MS MARCO-passage-shape synthetic 8.8M docs x 100K vocab, 1024-query batch, BM25 top-100"),
     "small": (100_000, 20_000, 60.0, 256, 10, "small smoke workload (not a bench line)"),
+    "c2s8": (125_000, 100_000, 60.0, 1024, 10,
+             "one rank's share of c2 at 8 GPUs on a single GPU: fixed per-step overheads (not a bench line)"),
 }
 FALLBACK_HBM_GBS = 6650.0
 

@@ -707,10 +707,10 @@ static I8Fused i8_fused_plan(int32_t n_q, int64_t n_docs, int dim, int k, bool s
     return p;
 }
 
-static size_t i8_fused_bytes(const I8Fused &fp, int64_t nq, int k) {
+static size_t i8_fused_bytes(const I8Fused &fp, int64_t nq, int /*k*/) {
     if (!fp.on) return 0;
     return align_up((size_t)nq * MM_MAX_GROUPS * 4, 256) + align_up((size_t)nq * 8, 256) +
-           align_up((size_t)nq * fp.cap * 8, 256) + align_up((size_t)nq * 4, 256) + topk_keys_ws_bytes(nq, fp.cap, k) + 256;
+           align_up((size_t)nq * fp.cap * 8, 256) + align_up((size_t)nq * 4, 256) + 256;
 }
 
 // enabled: 0 = plain chunked "dense tile + select" path; otherwise the fused-selection path (default)
@@ -770,8 +770,6 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
         uint64_t *thr = static_cast<uint64_t *>(carve((size_t)n_q * 8));
         uint64_t *cand = static_cast<uint64_t *>(carve((size_t)n_q * fp.cap * 8));
         int32_t *cand_cnt = static_cast<int32_t *>(carve((size_t)n_q * 4));
-        const size_t tkc_bytes = topk_keys_ws_bytes(n_q, fp.cap, k);
-        void *tkc = carve(tkc_bytes);
         // 1. threshold: every step-th 128-document tile is scanned with the MAXIMA epilogue (f32 approximation,
         //    one running maximum per thread and query); the k-th largest group maximum, lowered by the
         //    approximation margin, is a lower bound of the k-th best exact score
@@ -782,10 +780,9 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
         int rc = launch_int8_mma<MM_OUT_MAXIMA>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_SAMPLE, fp.step,
                                                 fp.n_sample, so, st, &gy);
         if (rc) return rc;
-        rc = kth_of_maxima(maxima, n_q, (int64_t)gy * MM_M, MM_MAX_GROUPS, k, true, thr, st);
+        rc = kth_of_maxima(maxima, n_q, (int64_t)gy * MM_M, MM_MAX_GROUPS, k, true, false, thr, st);
         if (rc) return rc;
         // 2. scan every tile, keep the documents whose exact key reaches the threshold
-        B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)n_q * fp.cap * 8, st));
         B2R_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)n_q * 4, st));
         MmOut fo = {};
         fo.thr_keys = thr;
@@ -797,7 +794,7 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
                                            st);
         if (rc) return rc;
         // 3. exact top-k of the candidates; overflowed queries fall through to the gated exhaustive path
-        rc = topk_keys_rows(cand, n_q, fp.cap, fp.cap, fp.cap, 0, k, keys, tkc, tkc_bytes, st);
+        rc = topk_of_lists(cand, n_q, fp.cap, cand_cnt, k, 0, keys, st);
         if (rc) return rc;
         gate.gate = cand_cnt;
         gate.gate_cap = fp.cap;

@@ -20,6 +20,7 @@
 // nothing synchronises.
 #include "common.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 namespace b2r {
@@ -282,7 +283,10 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         // at or below -inf (0x007fffff) there is nothing smaller: no filter
         uint32_t thr_ord = thr_hi > 0x007fffffu ? thr_hi - 1u : 0u;
         if (thr_ord == 0x7fffffffu) thr_ord = 0x7ffffffeu;
-        const double thr_lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
+        double thr_lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
+        // "strictly positive scores only" (kth_of_maxima's positive floor): nothing below 2^-150 rounds to a
+        // positive f32, so the untouched documents (acc == 0) never reach the conversion path
+        if (thr == ((0x80000000ull << 32) | 0xFFFFFFFFull)) thr_lo = __longlong_as_double(0x3690000000000000ll);
         // (measured: testing 8 documents per step through an fmax tree is slower than this plain pair loop)
         for (int i = lane * 2; i < sub; i += 64) {
             const double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
@@ -384,11 +388,16 @@ static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
     FusedPlan p = {};
     p.on = g_fused_enabled && !want_scores && k >= 1 && k <= FUSED_MAX_K && ix->n_tiles >= FUSED_MIN_TILES;
     if (!p.on) return p;
-    // The threshold is (about) the k-th best of a 1/step sample, so a query collects ~ k * step candidates
-    // (negative-binomial: sigma ~ sqrt(k) * step); the caps are > 6 sigma above that.
+    // The threshold is (about) the k-th best of a 1/r sample (r = n_tiles / n_sample <= step), so a query collects
+    // ~ k * r candidates (negative-binomial: sigma ~ sqrt(k) * r); the cap is the power of two above mean + 6 sigma.
     p.step = k <= 16 ? 64 : 16;
-    p.cap = k <= 16 ? 2048 : 4096;
     p.n_sample = (ix->n_tiles + p.step - 1) / p.step;
+    {
+        const double r = (double)ix->n_tiles / p.n_sample;
+        const double want = k * r + 6.0 * sqrt((double)k) * r + k;
+        p.cap = 256;
+        while (p.cap < want && p.cap < 4096) p.cap <<= 1;
+    }
     p.n_groups = (int64_t)p.n_sample * SC_GROUPS_PER_TILE;
     // tile 0 is full (n_tiles >= 8) and holds min(tile_docs / 2, 256) non-empty groups
     const int groups_tile0 = ix->tile_docs / 2 < SC_GROUPS_PER_TILE ? ix->tile_docs / 2 : SC_GROUPS_PER_TILE;
@@ -401,8 +410,7 @@ static size_t pass_bytes(const b2r_index *ix, const FusedPlan &fp, int64_t qc, i
     const size_t full = align_up((size_t)padded_docs(ix) * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k);
     if (!fp.on) return full;
     return full + align_up((size_t)fp.n_groups * 4 * (size_t)qc, 256) + align_up((size_t)qc * 8, 256) +
-           align_up((size_t)qc * fp.cap * 8, 256) + align_up((size_t)qc * 4, 256) + topk_keys_ws_bytes(qc, fp.cap, k) +
-           256;
+           align_up((size_t)qc * fp.cap * 8, 256) + align_up((size_t)qc * 4, 256) + 256;
 }
 
 }  // namespace b2r
@@ -522,17 +530,13 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
     const size_t tk_full_bytes = topk_ws_bytes(qc, ix->n_docs, k);
     void *tk_full = carve(tk_full_bytes);
     float *maxima = nullptr;
-    void *tk_cand = nullptr;
     uint64_t *thr = nullptr, *cand = nullptr;
     int32_t *cand_cnt = nullptr;
-    size_t tk_cand_bytes = 0;
     if (fp.on) {
         maxima = static_cast<float *>(carve((size_t)fp.n_groups * 4 * (size_t)qc));
         thr = static_cast<uint64_t *>(carve((size_t)qc * 8));
         cand = static_cast<uint64_t *>(carve((size_t)qc * fp.cap * 8));
         cand_cnt = static_cast<int32_t *>(carve((size_t)qc * 4));
-        tk_cand_bytes = topk_keys_ws_bytes(qc, fp.cap, k);
-        tk_cand = carve(tk_cand_bytes);
     }
 
     for (int64_t q0 = 0; q0 < n_queries; q0 += qc) {
@@ -547,10 +551,9 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             so.n_docs = (uint32_t)ix->n_docs;
             rc = launch_score<SC_OUT_MAXIMA>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
             if (rc) return rc;
-            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, thr, st);
+            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, true, thr, st);
             if (rc) return rc;
             // 2. every tile: score, keep only the documents that reach the threshold
-            B2R_CUDA(cudaMemsetAsync(cand, 0, (size_t)nq * fp.cap * 8, st));
             B2R_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * 4, st));
             ScoreOut fo = {};
             fo.thr_keys = thr;
@@ -564,7 +567,7 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             if (rc) return rc;
             if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[1], st));
             // 3. exact top-k of the candidates
-            rc = topk_keys_rows(cand, nq, fp.cap, fp.cap, fp.cap, 0, k, kout, tk_cand, tk_cand_bytes, st);
+            rc = topk_of_lists(cand, nq, fp.cap, cand_cnt, k, k, kout, st);
             if (rc) return rc;
             // 4. exact fallback, gated on the device to the queries whose list overflowed
             gate.gate = cand_cnt;

@@ -297,13 +297,49 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
     return topk_keys_rows(dst, n_rows, n2, n2, n2, 0, k, keys_out, wp, left, st, o2);
 }
 
+// ------------------------------------------------------------------------------ top-k of short lists
+// One CTA per row: the first min(cnt[row], cap) keys of the row's candidate list (the rest of the list is
+// never read, so it needs no clearing) are sorted in shared memory and the k best written out.
+constexpr int TL_THREADS = 256;
+constexpr int TL_MAX = 4096;  // longest list (32 KB of shared memory)
+
+__global__ void __launch_bounds__(TL_THREADS)
+topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__restrict__ cnt, int k, int min_cnt,
+                     uint64_t *__restrict__ out) {
+    __shared__ uint64_t arr[TL_MAX];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    int c = cnt[row];
+    __syncthreads();
+    // a list shorter than min_cnt cannot supply the k best (its threshold was raised above the sample's k-th
+    // best): mark the row for the exhaustive fallback exactly like an overflowed one (cnt > cap)
+    if (tid == 0 && c < min_cnt) cnt[row] = cap + 1;
+    c = c < 0 ? 0 : (c > cap ? cap : c);
+    int P = 32;
+    while (P < c || P < k) P <<= 1;
+    const uint64_t *src = lists + (int64_t)row * cap;
+    for (int i = tid; i < P; i += TL_THREADS) arr[i] = i < c ? src[i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc<TL_THREADS>(arr, P);
+    for (int i = tid; i < k; i += TL_THREADS) out[(int64_t)row * k + i] = arr[i];
+}
+
+int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
+                  uint64_t *keys_out, cudaStream_t st) {
+    if (n_rows == 0) return B2R_OK;
+    B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap, "top-k of lists: cap=%d / k=%d unsupported", cap, k);
+    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, 0, st>>>(lists, cap, cnt, k, min_cnt, keys_out);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
 // ------------------------------------------------------------------------------ k-th of group maxima
 // One CTA per row: radix select (4 passes of 8 bits over the ordered encoding) of the k-th largest of the
 // row's group maxima.  The rows are short (hundreds to a few ten thousand values) and stay in L1/L2.
 __global__ void __launch_bounds__(256)
 kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t row_stride, int k, int lower,
-                     uint64_t *__restrict__ thr_out) {
+                     int positive_floor, uint64_t *__restrict__ thr_out) {
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t wsum[8];
     __shared__ uint32_t s_prefix, s_k;
     const float *row = maxima + (int64_t)blockIdx.x * row_stride;
     const int tid = threadIdx.x;
@@ -316,15 +352,25 @@ kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t
             if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t above = 0;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (above + hist[b] >= kk) break;
-                above += hist[b];
+        {   // the bin holding the kk-th largest: suffix sums over the bins, high to low (thread t owns bin 255 - t)
+            const uint32_t v = hist[255 - tid];
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((tid & 31) >= o) inc += u;
             }
-            s_prefix = prefix | ((uint32_t)b << shift);
-            s_k = kk - above;
+            if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
+            inc += base;                               // values in bins >= mine
+            const uint32_t above = inc - v;            // values in bins > mine
+            // exactly one bin satisfies above < kk <= above + v; if fewer than kk values match, bin 0 takes it
+            if ((above < kk && inc >= kk) || (tid == 255 && inc < kk)) {
+                s_prefix = prefix | ((uint32_t)(255 - tid) << shift);
+                s_k = kk - above;
+            }
         }
         __syncthreads();
         prefix = s_prefix;
@@ -344,14 +390,20 @@ kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t
             o = ord_f32(tl);
             if (o <= 0x007fffffu) o = 0;
         }
-        thr_out[blockIdx.x] = (uint64_t)o << 32;
+        uint64_t thr = (uint64_t)o << 32;
+        // A sample whose k-th best is <= 0 (a query that matches few documents: untouched documents score exactly
+        // 0) would admit every document.  Keep only strictly positive scores instead; a query with fewer than k
+        // of them is caught by the short-list gate of topk_of_lists and rescored exhaustively.
+        if (positive_floor && o <= 0x80000000u) thr = (0x80000000ull << 32) | 0xFFFFFFFFull;
+        thr_out[blockIdx.x] = thr;
     }
 }
 
 int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
-                  uint64_t *thr_out, cudaStream_t st) {
+                  bool positive_floor, uint64_t *thr_out, cudaStream_t st) {
     if (n_rows == 0) return B2R_OK;
-    kth_of_maxima_kernel<<<(unsigned)n_rows, 256, 0, st>>>(maxima, n_groups, row_stride, k, lower ? 1 : 0, thr_out);
+    kth_of_maxima_kernel<<<(unsigned)n_rows, 256, 0, st>>>(maxima, n_groups, row_stride, k, lower ? 1 : 0,
+                                                           positive_floor ? 1 : 0, thr_out);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
