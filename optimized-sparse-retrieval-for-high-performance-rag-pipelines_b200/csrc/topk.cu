@@ -298,8 +298,36 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
 }
 
 // ------------------------------------------------------------------------------ top-k of short lists
-// One CTA per row: the first min(cnt[row], cap) keys of the row's candidate list (the rest of the list is
-// never read, so it needs no clearing) are sorted in shared memory and the k best written out.
+// Among 256 histogram bins (thread t owns bin 255 - t) find the bin that holds the kk-th largest value: suffix sums
+// high to low.  Returns through *bin / *kk_in_bin (shared); if fewer than kk values exist, bin 0 takes it.
+// Called by all 256 threads; contains barriers.
+__device__ __forceinline__ void select_bin_256(const uint32_t *hist, uint32_t kk, uint32_t *wsum, uint32_t *bin,
+                                               uint32_t *kk_in_bin) {
+    const int tid = threadIdx.x;
+    const uint32_t v = hist[255 - tid];
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += u;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
+    inc += base;                     // values in bins >= mine
+    const uint32_t above = inc - v;  // values in bins > mine
+    if ((above < kk && inc >= kk) || (tid == 255 && inc < kk)) {
+        *bin = 255u - (uint32_t)tid;
+        *kk_in_bin = kk - above;
+    }
+    __syncthreads();
+}
+
+// One CTA per row: the first min(cnt[row], cap) keys of the row's candidate list (the rest of the list is never
+// read, so it needs no clearing) are staged in shared memory; a radix select (8 passes of 8 bits) finds the k-th
+// largest key, the k keys at or above it are compacted and only those are sorted.  Keys are distinct (they carry
+// the document index), so exactly k survive.
 constexpr int TL_THREADS = 256;
 constexpr int TL_MAX = 4096;  // longest list (32 KB of shared memory)
 
@@ -307,6 +335,8 @@ __global__ void __launch_bounds__(TL_THREADS)
 topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__restrict__ cnt, int k, int min_cnt,
                      uint64_t *__restrict__ out) {
     __shared__ uint64_t arr[TL_MAX];
+    __shared__ uint64_t best[B2R_TOPK_MAX_FAST];
+    __shared__ uint32_t hist[256], wsum[8], s_bin, s_kk, s_n;
     const int row = blockIdx.x, tid = threadIdx.x;
     int c = cnt[row];
     __syncthreads();
@@ -314,13 +344,46 @@ topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__res
     // best): mark the row for the exhaustive fallback exactly like an overflowed one (cnt > cap)
     if (tid == 0 && c < min_cnt) cnt[row] = cap + 1;
     c = c < 0 ? 0 : (c > cap ? cap : c);
-    int P = 32;
-    while (P < c || P < k) P <<= 1;
     const uint64_t *src = lists + (int64_t)row * cap;
-    for (int i = tid; i < P; i += TL_THREADS) arr[i] = i < c ? src[i] : 0ull;
+    for (int i = tid; i < c; i += TL_THREADS) arr[i] = src[i];
+    uint64_t *sortbuf = arr;
+    int n = c;
+    if (c > k) {
+        uint64_t prefix = 0, mask = 0;
+        uint32_t kk = (uint32_t)k;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < c; i += TL_THREADS) {
+                const uint64_t key = arr[i];
+                if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            select_bin_256(hist, kk, wsum, &s_bin, &s_kk);
+            prefix |= (uint64_t)s_bin << shift;
+            kk = s_kk;
+            mask |= 255ull << shift;
+        }
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        for (int i = tid; i < c; i += TL_THREADS) {  // prefix is now the k-th largest key itself
+            const uint64_t key = arr[i];
+            if (key >= prefix) {
+                const uint32_t slot = atomicAdd(&s_n, 1u);
+                if (slot < (uint32_t)k) best[slot] = key;
+            }
+        }
+        __syncthreads();
+        sortbuf = best;
+        n = min((int)s_n, k);
+    }
+    int P = 32;
+    while (P < n || P < k) P <<= 1;  // P <= 1024 on the compacted path, <= TL_MAX otherwise (c <= k <= cap)
     __syncthreads();
-    bitonic_sort_desc<TL_THREADS>(arr, P);
-    for (int i = tid; i < k; i += TL_THREADS) out[(int64_t)row * k + i] = arr[i];
+    for (int i = n + tid; i < P; i += TL_THREADS) sortbuf[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc<TL_THREADS>(sortbuf, P);
+    for (int i = tid; i < k; i += TL_THREADS) out[(int64_t)row * k + i] = sortbuf[i];
 }
 
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
@@ -340,7 +403,7 @@ kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t
                      int positive_floor, uint64_t *__restrict__ thr_out) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t wsum[8];
-    __shared__ uint32_t s_prefix, s_k;
+    __shared__ uint32_t s_prefix, s_k, s_bin;
     const float *row = maxima + (int64_t)blockIdx.x * row_stride;
     const int tid = threadIdx.x;
     uint32_t prefix = 0, mask = 0, kk = (uint32_t)k;
@@ -352,26 +415,8 @@ kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t
             if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
         }
         __syncthreads();
-        {   // the bin holding the kk-th largest: suffix sums over the bins, high to low (thread t owns bin 255 - t)
-            const uint32_t v = hist[255 - tid];
-            uint32_t inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((tid & 31) >= o) inc += u;
-            }
-            if ((tid & 31) == 31) wsum[tid >> 5] = inc;
-            __syncthreads();
-            uint32_t base = 0;
-            for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
-            inc += base;                               // values in bins >= mine
-            const uint32_t above = inc - v;            // values in bins > mine
-            // exactly one bin satisfies above < kk <= above + v; if fewer than kk values match, bin 0 takes it
-            if ((above < kk && inc >= kk) || (tid == 255 && inc < kk)) {
-                s_prefix = prefix | ((uint32_t)(255 - tid) << shift);
-                s_k = kk - above;
-            }
-        }
+        select_bin_256(hist, kk, wsum, &s_bin, &s_k);
+        if (tid == 0) s_prefix = prefix | (s_bin << shift);
         __syncthreads();
         prefix = s_prefix;
         kk = s_k;
