@@ -242,6 +242,16 @@ int b2r_int8_rerank(const int64_t *cand_idx, const float *cand_sparse, int32_t n
                     int64_t doc_id_base, float sparse_weight, float dense_weight, int32_t k_out, float *dense_out,
                     int64_t *idx_out, float *val_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* fp32 dense similarity + top-k: scores[q, r] = <emb[r, :], queries[q, :]> over a row-major f32[n_rows, dim]
+ * matrix resident on the device, then the k best rows per query (reference: RetrievalService.search_by_vector,
+ * rag_system/core/retrieval.py:402-436 -- np.dot through host BLAS + fast_topk_selection).  f32 products and
+ * f32 pairwise sums: parity with BLAS is by tolerance (1e-5 * sum |a_i b_i|), the selection is exact on the
+ * computed scores.  scores_out: optional f32[n_q, scores_stride] (then k may be 0); idx/val as everywhere. */
+int b2r_f32_dot_topk_workspace(int32_t n_q, int64_t n_rows, int32_t k, size_t *bytes);
+int b2r_f32_dot_topk(const float *emb, int64_t n_rows, int32_t dim, const float *queries, int32_t n_q, int32_t k,
+                     int64_t doc_id_base, float *scores_out, int64_t scores_stride, int64_t *idx_out, float *val_out,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

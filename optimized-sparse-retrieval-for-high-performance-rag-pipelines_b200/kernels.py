@@ -51,7 +51,7 @@ def set_int8_fused(mode) -> None:
 
 __all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_bank_schedule", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
-           "int8_scan_topk", "int8_rerank", "hybrid_search"]
+           "int8_scan_topk", "int8_rerank", "hybrid_search", "dense_topk"]
 
 # key -> (index, the source arrays: holding them keeps their addresses from being reused)
 _INDEX_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -195,6 +195,34 @@ def int8_scan_topk(queries_int8, corpus_int8, query_scales, corpus_scales, k: in
                                            int(doc_id_base), keys.data_ptr(), idx.data_ptr(), val.data_ptr(),
                                            ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "int8 scan")
     return idx, val, keys
+
+
+def dense_topk(embeddings, query_vectors, k: int, *, doc_id_base: int = 0, return_scores: bool = False):
+    """fp32 similarities <embeddings[r], query> + top-k on the GPU (reference: search_by_vector, retrieval.py:402-436,
+    np.dot through host BLAS).  `embeddings` f32[N, D] (a CUDA tensor stays where it is; anything else is uploaded),
+    `query_vectors` f32[D] or f32[Q, D].  Returns CUDA tensors (idx i64[Q, k], val f32[Q, k][, scores f32[Q, N]])."""
+    dev = _cuda_device(embeddings.device if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda else None)
+    emb = _to_device(embeddings, torch.float32, dev)
+    q = _to_device(query_vectors, torch.float32, dev)
+    if q.dim() == 1:
+        q = q[None, :]
+    if emb.dim() != 2 or q.dim() != 2 or q.shape[1] != emb.shape[1]:
+        raise ValueError("embeddings [N, D] and query_vectors [Q, D] must share D")
+    n, dim, nq = int(emb.shape[0]), int(emb.shape[1]), int(q.shape[0])
+    k = min(int(k), n)
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    nbytes = C.c_size_t(0)
+    _abi.check(_abi.lib.b2r_f32_dot_topk_workspace(nq, n, k, C.byref(nbytes)), "dense top-k workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    stride = (n + 3) // 4 * 4
+    scores = torch.empty((nq, stride), dtype=torch.float32, device=dev) if return_scores else None
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    _abi.check(_abi.lib.b2r_f32_dot_topk(emb.data_ptr(), n, dim, q.data_ptr(), nq, k, int(doc_id_base),
+                                         scores.data_ptr() if scores is not None else None, stride, idx.data_ptr(),
+                                         val.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "dense top-k")
+    return (idx, val, scores[:, :n]) if return_scores else (idx, val)
 
 
 def int8_rerank(cand_idx, cand_sparse, queries_int8, query_scales, corpus_int8, corpus_scales, k_out: int, *,

@@ -24,7 +24,7 @@ from scipy.sparse import csr_matrix
 
 from .docstore import Document, MemoryIndex
 from .index import TermMajorIndex, pack_queries, reference_avgdl, reference_idf
-from .kernels import fast_topk_selection
+from .kernels import dense_topk, fast_topk_selection
 
 logger = logging.getLogger(__name__)
 _WORD = re.compile(r"\b\w+\b")
@@ -58,6 +58,7 @@ class RetrievalService:
         self._gpu_params: Optional[tuple] = None
 
         self.embedding_index = None
+        self._gpu_embeddings = None
         if self.embedding_path and self.embedding_path.exists():
             self._load_embeddings()
 
@@ -257,21 +258,26 @@ class RetrievalService:
             if n > 0:
                 dim = self.embedding_path.stat().st_size // (n * 4)
                 self.embedding_index = np.memmap(self.embedding_path, dtype="float32", mode="r", shape=(n, dim))
+                self._gpu_embeddings = None
         except Exception as e:  # pragma: no cover
             self.logger.error("Error loading embeddings: %s", e)
             self.embedding_index = None
 
     def search_by_vector(self, query_vector: np.ndarray, k: int = 10, min_score: float = 0.0) -> List[Dict]:
-        """retrieval.py:402-436: fp32 similarities (host BLAS, as in the reference) + GPU top-k."""
+        """retrieval.py:402-436: fp32 similarities + top-k + min_score cut-off.  The reference runs np.dot over
+        the memmap through host BLAS; here the embedding matrix is uploaded to HBM once and b2r_f32_dot_topk
+        does the gemv and the selection (scores agree with BLAS within f32 summation-order tolerance)."""
         if self.embedding_index is None:
             raise ValueError("No embedding index available")
-        sims = np.dot(self.embedding_index, query_vector).astype(np.float32)
-        idx, val = fast_topk_selection(sims, k)
+        if self._gpu_embeddings is None:
+            import torch
+            self._gpu_embeddings = torch.from_numpy(np.array(self.embedding_index, dtype=np.float32, order="C")).cuda()
+        idx, val = dense_topk(self._gpu_embeddings, np.asarray(query_vector, dtype=np.float32), k)
         out = []
-        for i, s in zip(idx, val):
+        for i, s in zip(idx[0].cpu().numpy(), val[0].cpu().numpy()):
             if s < min_score:
                 break
-            if i < len(self.doc_ids):
+            if 0 <= i < len(self.doc_ids):
                 out.append({"doc_id": self.doc_ids[int(i)], "score": float(s)})
         return out
 

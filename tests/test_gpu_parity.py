@@ -228,6 +228,47 @@ def test_hybrid_search_two_stage(b2r):
     assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(_bits(gv.cpu().numpy()), _bits(wv))
 
 
+@pytest.mark.parametrize("n,dim,nq", [(20_000, 768, 1), (5003, 100, 11), (300, 7, 3)])
+def test_dense_topk_vs_numpy(b2r, n, dim, nq):
+    """a8 (search_by_vector): fp32 gemv + top-k.  BLAS fixes no summation order, so the scores are held to the
+    dot-product error scale (1e-5 * sum |a_i b_i|, in practice a few ulp) against an f64 evaluation; the selection
+    must be exact on the scores the kernel produced."""
+    rng = np.random.default_rng(81 + dim)
+    emb = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    k = 10
+    idx, val, sc = b2r.dense_topk(emb, q if nq > 1 else q[0], k, return_scores=True)
+    sc, idx, val = sc.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
+    exact = emb.astype(np.float64) @ q.astype(np.float64).T
+    scale = np.abs(emb).astype(np.float64) @ np.abs(q).astype(np.float64).T
+    assert np.all(np.abs(sc.T - exact) <= 1e-5 * scale + 1e-30)
+    assert np.all(np.abs(sc.T - (emb @ q.T)) <= 2e-5 * scale + 1e-30)          # the reference's np.dot (f32 BLAS)
+    for i in range(nq):
+        wi, wv = np_oracle.topk_canonical(sc[i], k)
+        assert np.array_equal(idx[i], wi) and np.array_equal(_bits(val[i]), _bits(wv))
+
+
+def test_service_search_by_vector(b2r, tmp_path):
+    rng = np.random.default_rng(91)
+    n, dim = 500, 64
+    emb = rng.standard_normal((n, dim)).astype(np.float32)
+    emb.tofile(tmp_path / "emb.f32")
+    store = tmp_path / "docs.idx"
+    b2r.MemoryIndex(store, create=True).close()
+    svc = b2r.RetrievalService(store, embedding_path=tmp_path / "emb.f32")
+    with pytest.raises(ValueError, match="No embedding index"):
+        svc.search_by_vector(emb[0])                       # like the reference: nothing is mapped before doc_ids exist
+    svc.doc_ids = [f"d{i}" for i in range(n)]
+    svc._load_embeddings()
+    got = svc.search_by_vector(emb[17], k=5)
+    sims = emb @ emb[17]
+    assert got[0]["doc_id"] == "d17" and len(got) == 5
+    assert [g["doc_id"] for g in got] == [f"d{i}" for i in np.argsort(-sims)[:5]]
+    assert np.allclose([g["score"] for g in got], np.sort(sims)[::-1][:5], rtol=1e-5)
+    cut = float(np.sort(sims)[::-1][2])
+    assert len(svc.search_by_vector(emb[17], k=5, min_score=cut - 1e-4)) == 3
+
+
 # ----------------------------------------------------------------------------------- golden + edge: K2
 def test_topk_reference_cases(b2r, golden_dir):
     z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
