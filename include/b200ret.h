@@ -216,6 +216,9 @@ void b2r_set_int8_mma(int enabled);
 /* Test / profiling hook: largest thread-block cluster (1, 2, 4 or 8 query-tile CTAs sharing every document
  * chunk by TMA multicast) the tcgen05 kernel may use; 1 = no clusters. */
 void b2r_set_int8_cluster(int max_cluster);
+/* Test / profiling hook: 1 = the fused scan of batches of more than 128 queries runs on CTA pairs
+ * (tcgen05.mma cta_group::2, 256 documents x 256 queries per pair tile); 0 = single-CTA 128 x 128 tiles. */
+void b2r_set_int8_pair(int enabled);
 /* Test / profiling hook: 0 = b2r_int8_scan_topk uses the plain chunked "dense tile + select" path;
  * otherwise (default) the fused-selection path: sampled threshold, f32 pre-filter + exact f64 check in the
  * MMA epilogue, candidate lists, device-gated exact fallback. */

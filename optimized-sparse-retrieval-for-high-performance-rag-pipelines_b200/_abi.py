@@ -110,6 +110,7 @@ SIGNATURES = {
     "b2r_int8_dot_batch": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _P, _P]),
     "b2r_set_int8_mma": (None, [C.c_int]),
     "b2r_set_int8_cluster": (None, [C.c_int]),
+    "b2r_set_int8_pair": (None, [C.c_int]),
     "b2r_set_int8_fused": (None, [C.c_int]),
     "b2r_int8_scan_workspace": (C.c_int, [_I32, _I64, _I32, _I32, C.POINTER(_SZ)]),
     "b2r_f32_dot_topk_workspace": (C.c_int, [_I32, _I64, _I32, C.POINTER(_SZ)]),

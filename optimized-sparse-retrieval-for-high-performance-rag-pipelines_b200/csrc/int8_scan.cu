@@ -537,6 +537,245 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// =================================================================================================
+// CTA-pair variant of the fused scan (tcgen05.mma cta_group::2, M = 256 documents x N = 256 queries)
+// =================================================================================================
+// The 128 x 128 single-CTA tile is bound by shared-memory bandwidth: per tile the tensor core fetches 192 KB of
+// operands from shared memory while TMA writes 96 KB into it (profiles: the pipeline runs at the SUM of the TMA and
+// MMA times).  A CTA pair (two SMs of one TPC, cluster of 2 along x) halves both per output: CTA r holds the
+// query rows [q0 + 128 r, +128) resident (its half of the N = 256 operand), streams its own 128-document tile
+// (its half of the M = 256 operand) and receives a 128 x 256 accumulator in its own TMEM.  Only the leader
+// (cluster rank 0) issues MMAs; TMA completions of both CTAs are counted on the leader's barriers; MMA commits
+// are multicast to both; both epilogues release the accumulator on the leader's barrier.
+constexpr int MP_N = 256;  // queries per pair tile = accumulator columns per CTA
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {  // same offset in CTA `cta` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into MY shared memory whose completion is counted on a barrier given by its shared::cluster address
+// (the leader's): the .cta_group::2 form allows destination and barrier to live in different CTAs of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                                 uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_s8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {  // both CTAs' barrier at this offset
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(MM_THREADS, 1)
+int8_mma_pair_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_q, int n_q,
+                     int64_t n_docs, int n_kc, int n_stages, const float *__restrict__ q_scale,
+                     const float *__restrict__ d_scale, int64_t n_pairs, MmOut o) {
+    extern __shared__ uint8_t mm_smem_raw[];
+    __shared__ MmBars bars;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ double qs_s[MP_N];
+    __shared__ uint64_t thr_key_s[MP_N];
+    __shared__ float2 flt_s[MP_N];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(mm_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sB = smem;                          // [n_kc][my 128 queries][128 B]
+    uint8_t *sA = smem + n_kc * MM_CHUNK_BYTES;  // [n_stages][my 128 docs][128 B]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();     // 0 = leader
+    const int q0 = (int)(blockIdx.x >> 1) * MP_N;  // first query of the pair tile
+    auto doc_tile = [&](int64_t t) -> int64_t { return 2 * t + rank; };  // my 128-document tile of pair tile t
+
+    if (warp == 0) {  // one warp of EACH CTA of the pair takes part in the allocation
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)(2 * MP_N))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < MM_MAX_STAGES; ++i) {
+            mbar_init(&bars.full[i], 1);   // (used on the leader) its own arrive.expect_tx; bytes of both CTAs
+            mbar_init(&bars.empty[i], 1);  // the leader's multicast commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars.tfull[i], 1);                    // the leader's multicast commit
+            mbar_init(&bars.tempty[i], 2 * MM_EPI_WARPS);    // (used on the leader) every epilogue warp of the pair
+        }
+        mbar_init(&bars.bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < MP_N; i += MM_THREADS) {
+        const bool qv = q0 + i < n_q;
+        const float qf = qv ? q_scale[q0 + i] : 0.0f;
+        qs_s[i] = (double)qf;
+        const uint64_t thr = qv ? o.thr_keys[q0 + i] : ~0ull;
+        const uint32_t hi = (uint32_t)(thr >> 32);
+        thr_key_s[i] = thr;
+        const float thr_f = hi ? unord_f32(hi) : __int_as_float(0xff800000);
+        const bool sane = fabsf(qf) >= 1e-15f && fabsf(qf) <= 1e15f && hi != 0 && fabsf(thr_f) <= 3e38f;
+        float lo_f = sane ? __fsub_rn(__fsub_rn(thr_f, __fmul_rn(fabsf(thr_f), 9.5367431640625e-07f)), 1e-37f)
+                          : __int_as_float(0xff800000);
+        if (!qv) lo_f = __int_as_float(0x7f800000);
+        flt_s[i] = make_float2(qf, lo_f);  // (see int8_mma_kernel for the pre-filter's error bound)
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers and TMEM are set up before any remote signal
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == MM_EPI_WARPS) {
+        if (lane == 0) {  // ---- TMA producer (both CTAs): completions are counted on the LEADER's barriers
+            const uint32_t bfull_l = mapa_u32(smem_u32(&bars.bfull), 0);
+            if (rank == 0) mbar_expect_tx(&bars.bfull, (uint32_t)(2 * n_kc * MM_CHUNK_BYTES));
+            for (int kc = 0; kc < n_kc; ++kc)
+                tma_load_2d_pair(sB + kc * MM_CHUNK_BYTES, &map_q, kc * MM_KC, q0 + (int)rank * MM_N, bfull_l);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int64_t t = blockIdx.y; t < n_pairs; t += gridDim.y) {
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(smem_u32(&bars.empty[stage]), ph ^ 1);  // my slot is free (leader's MMAs done with it)
+                    if (rank == 0) mbar_expect_tx(&bars.full[stage], (uint32_t)(2 * MM_CHUNK_BYTES));
+                    tma_load_2d_pair(sA + stage * MM_CHUNK_BYTES, &map_d, kc * MM_KC, (int)(doc_tile(t) * MM_M),
+                                     mapa_u32(smem_u32(&bars.full[stage]), 0));
+                    if (++stage == n_stages) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == MM_EPI_WARPS + 1) {
+        if (lane == 0 && rank == 0) {  // ---- MMA issuer (leader only): 256 x 256 x 32 per instruction
+            const uint32_t idesc = umma_idesc_s8(2 * MM_M, MP_N);
+            mbar_wait(smem_u32(&bars.bfull), 0);
+            int stage = 0, acc = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int64_t t = blockIdx.y; t < n_pairs; t += gridDim.y) {
+                mbar_wait(smem_u32(&bars.tempty[acc]), acc_ph ^ 1);  // both epilogues drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MP_N);
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(smem_u32(&bars.full[stage]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int ks = 0; ks < MM_KC / MM_UK; ++ks) {
+                        const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * MM_CHUNK_BYTES + ks * MM_UK));
+                        const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * MM_CHUNK_BYTES + ks * MM_UK));
+                        if (o.diag < 2) umma_s8_pair(d_tmem, ad, bd, idesc, (kc | ks) ? 1u : 0u);
+                    }
+                    umma_commit_pair(&bars.empty[stage]);  // frees the slot in both CTAs
+                    if (++stage == n_stages) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
+                }
+                umma_commit_pair(&bars.tfull[acc]);  // accumulator complete in both CTAs
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_ph ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {  // ---- epilogue warps: TMEM lane quadrant = warp % 4, column group of 64 = warp / 4
+        const int quad = warp & 3, cg = warp >> 2;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        auto scale_of = [&](int64_t t) -> float {
+            const int64_t d = doc_tile(t) * MM_M + quad * 32 + lane;
+            return (t < n_pairs && d < n_docs) ? __ldg(d_scale + d) : 0.0f;
+        };
+        float dsf_next = scale_of(blockIdx.y);
+        for (int64_t t = blockIdx.y; t < n_pairs; t += gridDim.y) {
+            const int64_t doc = doc_tile(t) * MM_M + quad * 32 + lane;
+            const bool doc_ok = doc < n_docs;
+            const float dsf = dsf_next;
+            dsf_next = scale_of(t + gridDim.y);
+            const double ds = (double)dsf;
+            const bool ds_sane = fabsf(dsf) >= 1e-15f && fabsf(dsf) <= 1e15f;
+            mbar_wait(smem_u32(&bars.tfull[acc]), acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int cc = o.diag >= 1 ? 2 : 0; cc < 2; ++cc) {  // (B2R_INT8_DIAG >= 1: release the accumulator unread)
+                const int c0 = cg * 64 + cc * 32;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * MP_N + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t hit = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 f = flt_s[c0 + j];
+                    const float p = __fmul_rn(__fmul_rn((float)(int32_t)v[j], f.x), dsf);
+                    hit |= (p < f.y) ? 0u : (1u << j);  // NaN passes
+                }
+                if (!ds_sane) hit = 0xffffffffu;
+                if (!doc_ok) hit = 0;
+                uint32_t cols = __reduce_or_sync(0xffffffffu, hit);
+                while (cols) {  // exact f64 chain for the survivors, column by column (re-read from TMEM)
+                    const int j = __ffs(cols) - 1;
+                    cols &= cols - 1;
+                    uint32_t dot;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dot) : "r"(taddr + (uint32_t)j));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if ((hit >> j) & 1u) {
+                        const float sc = __double2float_rn(__dmul_rn(__dmul_rn((double)(int32_t)dot, qs_s[c0 + j]), ds));
+                        const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
+                        if (key > thr_key_s[c0 + j]) {
+                            const int q = q0 + c0 + j;
+                            const int slot = atomicAdd(o.cand_cnt + q, 1);
+                            if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
+                        }
+                    }
+                }
+            }
+            // done with this accumulator buffer: tell the leader's MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars.tempty[acc]), 0));
+            if (++acc == 2) {
+                acc = 0;
+                acc_ph ^= 1;
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it or read its shared memory
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * MP_N))
+                     : "memory");
+    }
+}
+
 static int make_rowmajor_i8_map(CUtensorMap *map, const int8_t *base, int64_t n_rows, int dim) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -630,6 +869,55 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
     return B2R_OK;
 }
 
+static int g_int8_pair = 1;  // 1 = the fused scan of batches > 128 queries runs on CTA pairs (cta_group::2)
+
+// fused scan of all documents on CTA pairs; same contract as launch_int8_mma<MM_OUT_FUSED>(MM_TILES_ALL)
+static int launch_int8_pair(const int8_t *q8, int n_q, const int8_t *d8, int64_t n_docs, int dim, const float *qs,
+                            const float *ds, const MmOut &o, cudaStream_t st) {
+    if (n_q == 0 || n_docs == 0) return B2R_OK;
+    const int n_kc = dim / MM_KC;
+    const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M, n_pairs = (n_tiles + 1) / 2;
+    // ring depth: what 227 KB leave next to my half of the query tile, the static arrays (~6.3 KB) and alignment
+    int n_stages = (232448 - 7168 - 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
+    if (n_stages > MM_MAX_STAGES) n_stages = MM_MAX_STAGES;
+    const size_t smem = (size_t)(n_kc + n_stages) * MM_CHUNK_BYTES + 1024;
+    CUtensorMap map_d, map_q;
+    int rc = make_rowmajor_i8_map(&map_d, d8, n_docs, dim);
+    if (rc) return rc;
+    rc = make_rowmajor_i8_map(&map_q, q8, n_q, dim);
+    if (rc) return rc;
+    B2R_CUDA(cudaFuncSetAttribute(int8_mma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_qt = (n_q + MP_N - 1) / MP_N;  // pair tiles along the queries; grid x = 2 CTAs per pair tile
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(MM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(2 * n_qt), 1);
+    int max_clusters = 0;  // persistent kernel: one wave of CTA pairs
+    B2R_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, int8_mma_pair_kernel, &cfg));
+    if (max_clusters < 1) max_clusters = 1;
+    int64_t gy = (int64_t)max_clusters / n_qt;
+    if (gy < 1) gy = 1;
+    if (gy > n_pairs) gy = n_pairs;
+    cfg.gridDim = dim3((unsigned)(2 * n_qt), (unsigned)gy);
+    static const int diag = [] {
+        const char *e = getenv("B2R_INT8_DIAG");
+        return e ? atoi(e) : 0;
+    }();
+    MmOut od = o;
+    od.diag = diag;
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, int8_mma_pair_kernel, map_d, map_q, n_q, n_docs, n_kc, n_stages, qs, ds, n_pairs, od));
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
 static bool g_int8_use_mma = true;
 
 // dense scores of all documents; `gate` (optional) restricts the work to queries with gate[q] > gate_cap
@@ -673,6 +961,7 @@ using namespace b2r;
 // test / profiling hooks: b2r_set_int8_mma(0) forces the dp4a kernel for every shape;
 // b2r_set_int8_cluster(c) caps the thread-block cluster (TMA multicast group) of the tcgen05 kernel at c CTAs
 extern "C" void b2r_set_int8_mma(int enabled) { b2r::g_int8_use_mma = enabled != 0; }
+extern "C" void b2r_set_int8_pair(int enabled) { b2r::g_int8_pair = enabled != 0; }
 extern "C" void b2r_set_int8_cluster(int max_cluster) {
     b2r::g_int8_cluster = max_cluster < 1 ? 1 : max_cluster > 8 ? 8 : max_cluster;
 }
@@ -790,8 +1079,11 @@ extern "C" int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d
         fo.cand_cnt = cand_cnt;
         fo.cap = fp.cap;
         fo.doc_id_base = (uint32_t)doc_id_base;
-        rc = launch_int8_mma<MM_OUT_FUSED>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_ALL, 1, fp.n_tiles, fo,
-                                           st);
+        if (g_int8_pair && n_q > MM_N)
+            rc = launch_int8_pair(q8, n_q, d8, n_docs, dim, q_scale, d_scale, fo, st);
+        else
+            rc = launch_int8_mma<MM_OUT_FUSED>(q8, n_q, d8, n_docs, dim, q_scale, d_scale, MM_TILES_ALL, 1, fp.n_tiles,
+                                               fo, st);
         if (rc) return rc;
         // 3. exact top-k of the candidates; overflowed queries fall through to the gated exhaustive path
         rc = topk_of_lists(cand, n_q, fp.cap, cand_cnt, k, 0, keys, st);

@@ -38,6 +38,12 @@ def set_int8_cluster(max_cluster: int) -> None:
     _abi.lib.b2r_set_int8_cluster(int(max_cluster))
 
 
+def set_int8_pair(enabled: bool) -> None:
+    """Profiling / test hook: True runs the fused INT8 scan of batches > 128 queries on CTA pairs (cta_group::2).
+    Results are identical."""
+    _abi.lib.b2r_set_int8_pair(1 if enabled else 0)
+
+
 def set_bank_schedule(enabled: bool) -> None:
     """Profiling / test hook: False makes later index builds keep dense segments doc-ascending."""
     _abi.lib.b2r_set_bank_schedule(1 if enabled else 0)
@@ -49,7 +55,7 @@ def set_int8_fused(mode) -> None:
     _abi.lib.b2r_set_int8_fused(int(mode))
 
 
-__all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_bank_schedule", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
+__all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_int8_pair", "set_bank_schedule", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
            "int8_scan_topk", "int8_rerank", "hybrid_search", "dense_topk"]
 

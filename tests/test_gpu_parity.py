@@ -23,6 +23,9 @@ def b2r():
     return b200ret
 
 
+PAIR_DEFAULT = True      # default of b2r_set_int8_pair in the library (restored after tests that flip it)
+
+
 def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
@@ -267,6 +270,35 @@ def test_service_search_by_vector(b2r, tmp_path):
     assert np.allclose([g["score"] for g in got], np.sort(sims)[::-1][:5], rtol=1e-5)
     cut = float(np.sort(sims)[::-1][2])
     assert len(svc.search_by_vector(emb[17], k=5, min_score=cut - 1e-4)) == 3
+
+
+@pytest.mark.parametrize("nq,n", [(130, 70_000 + 13), (512, 40_000), (257, 33_000 + 129)])
+def test_int8_pair_scan_equals_single_cta_and_oracle(b2r, nq, n):
+    """CTA-pair fused scan (tcgen05.mma cta_group::2, 256 x 256 pair tiles) vs the single-CTA fused scan vs exact
+    integer math: odd query counts (zero-padded operand halves), an odd number of 128-document tiles (the second
+    CTA of the last pair sees only padding), overflowing candidate lists."""
+    rng = np.random.default_rng(101 + nq)
+    dim, k = 768, 100
+    q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+    d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
+    qs = (rng.random(nq).astype(np.float32) + 0.01) / 127
+    ds = rng.random(n).astype(np.float32) + 0.01
+    d8_adv = d8.copy()
+    d8_adv[((np.arange(n) // 128) % 16) == 0] = 0           # useless threshold: candidate lists overflow
+    for corpus in (d8, d8_adv):
+        try:
+            b2r.set_int8_pair(True)
+            pi, pv, _ = b2r.int8_scan_topk(q8, corpus, qs, ds, k, doc_id_base=7)
+            b2r.set_int8_pair(False)
+            si, sv, _ = b2r.int8_scan_topk(q8, corpus, qs, ds, k, doc_id_base=7)
+        finally:
+            b2r.set_int8_pair(PAIR_DEFAULT)
+        assert torch.equal(pi, si) and torch.equal(pv, sv)
+        for q in (0, 127, 128, nq - 1):
+            want = np_oracle.int8_dot_batch(q8[q:q + 1], corpus, qs[q:q + 1], ds)[0]
+            wi, wv = np_oracle.topk_canonical(want, k)
+            assert np.array_equal(pi[q].cpu().numpy(), wi + 7)
+            assert np.array_equal(_bits(pv[q].cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
 
 
 # ----------------------------------------------------------------------------------- golden + edge: K2

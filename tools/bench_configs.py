@@ -91,6 +91,8 @@ def run_int8(args):
     d8 = torch.randint(-127, 128, (n, dim), device=dev, dtype=torch.int8, generator=g)
     ds = torch.rand(n, device=dev, generator=g) + 0.01
     out = []
+    if args.pair is not None:
+        b200ret.set_int8_pair(bool(args.pair))
     for nq, cl, fm in [(a, b, c) for a in args.queries for b in (args.clusters or [None])
                        for c in (args.fused_modes or [None])]:
         if cl is not None:
@@ -108,6 +110,8 @@ def run_int8(args):
             rec["max_cluster"] = cl
         if fm is not None:
             rec["fused_mode"] = fm
+        if args.pair is not None:
+            rec["cta_pair"] = args.pair
         if nq <= 64 and n <= 2_000_000:    # parity spot check on the first query against exact integer math
             idx, val, _ = b200ret.int8_scan_topk(q8[:1], d8, qs[:1], ds, k)
             dots = (d8.to(torch.int32) * q8[0].to(torch.int32)).sum(1).to(torch.float64)
@@ -260,6 +264,7 @@ def main():
     ap.add_argument("--queries", type=int, nargs="+", default=[1, 64, 1024])
     ap.add_argument("--check", type=int, default=1)
     ap.add_argument("--k", type=int, default=100, help="int8: top-k")
+    ap.add_argument("--pair", type=int, default=None, help="int8: 1 = CTA-pair (cta_group::2) fused scan, 0 = single CTA")
     ap.add_argument("--fused-modes", type=int, nargs="*", default=None,
                     help="int8: sweep b2r_set_int8_fused (0 plain, 1 default gate, 2 fused for every batch size)")
     ap.add_argument("--clusters", type=int, nargs="*", default=None,
