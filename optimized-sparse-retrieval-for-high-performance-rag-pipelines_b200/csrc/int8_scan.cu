@@ -593,6 +593,10 @@ int8_mma_pair_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_con
     __shared__ double qs_s[MP_N];
     __shared__ uint64_t thr_key_s[MP_N];
     __shared__ float2 flt_s[MP_N];
+    // survivors are staged per warp and appended to the global candidate lists 32 at a time, so that the
+    // round trip of the global atomics is paid once per 32 survivors and not on every accumulator release
+    __shared__ uint64_t stage_key[MM_EPI_WARPS][64];
+    __shared__ int32_t stage_q[MM_EPI_WARPS][64];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(mm_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sB = smem;                          // [n_kc][my 128 queries][128 B]
     uint8_t *sA = smem + n_kc * MM_CHUNK_BYTES;  // [n_stages][my 128 docs][128 B]
@@ -703,6 +707,7 @@ int8_mma_pair_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_con
             return (t < n_pairs && d < n_docs) ? __ldg(d_scale + d) : 0.0f;
         };
         float dsf_next = scale_of(blockIdx.y);
+        int n_staged = 0;  // survivors in my warp's staging buffer (warp-uniform)
         for (int64_t t = blockIdx.y; t < n_pairs; t += gridDim.y) {
             const int64_t doc = doc_tile(t) * MM_M + quad * 32 + lane;
             const bool doc_ok = doc < n_docs;
@@ -744,13 +749,34 @@ int8_mma_pair_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_con
                     uint32_t dot;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dot) : "r"(taddr + (uint32_t)j));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    bool pass = false;
+                    uint64_t key = 0;
                     if ((hit >> j) & 1u) {
                         const float sc = __double2float_rn(__dmul_rn(__dmul_rn((double)(int32_t)dot, qs_s[c0 + j]), ds));
-                        const uint64_t key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
-                        if (key > thr_key_s[c0 + j]) {
-                            const int q = q0 + c0 + j;
-                            const int slot = atomicAdd(o.cand_cnt + q, 1);
-                            if (slot < o.cap) o.cand[(int64_t)q * o.cap + slot] = key;
+                        key = make_key(ord_f32(sc), o.doc_id_base + (uint32_t)doc);
+                        pass = key > thr_key_s[c0 + j];
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                    if (m) {  // warp-uniform: append to my warp's staging buffer (n_staged <= 31 before, <= 63 after)
+                        if (pass) {
+                            const int slot = n_staged + __popc(m & ((1u << lane) - 1u));
+                            stage_key[warp][slot] = key;
+                            stage_q[warp][slot] = q0 + c0 + j;
+                        }
+                        n_staged += __popc(m);
+                        __syncwarp();
+                        if (n_staged >= 32) {  // flush 32 survivors: one global atomic per lane, all in flight together
+                            const uint64_t fk = stage_key[warp][lane];
+                            const int fq = stage_q[warp][lane];
+                            const int gslot = atomicAdd(o.cand_cnt + fq, 1);
+                            if (gslot < o.cap) o.cand[(int64_t)fq * o.cap + gslot] = fk;
+                            const uint64_t mk = stage_key[warp][32 + lane];
+                            const int mq = stage_q[warp][32 + lane];
+                            __syncwarp();
+                            stage_key[warp][lane] = mk;  // move the tail (n_staged - 32 <= 31 entries) to the front
+                            stage_q[warp][lane] = mq;
+                            n_staged -= 32;
+                            __syncwarp();
                         }
                     }
                 }
@@ -763,6 +789,12 @@ int8_mma_pair_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_con
                 acc = 0;
                 acc_ph ^= 1;
             }
+        }
+        if (lane < n_staged) {  // what is left in the staging buffer
+            const uint64_t fk = stage_key[warp][lane];
+            const int fq = stage_q[warp][lane];
+            const int gslot = atomicAdd(o.cand_cnt + fq, 1);
+            if (gslot < o.cap) o.cand[(int64_t)fq * o.cap + gslot] = fk;
         }
     }
 
@@ -877,8 +909,8 @@ static int launch_int8_pair(const int8_t *q8, int n_q, const int8_t *d8, int64_t
     if (n_q == 0 || n_docs == 0) return B2R_OK;
     const int n_kc = dim / MM_KC;
     const int64_t n_tiles = (n_docs + MM_M - 1) / MM_M, n_pairs = (n_tiles + 1) / 2;
-    // ring depth: what 227 KB leave next to my half of the query tile, the static arrays (~6.3 KB) and alignment
-    int n_stages = (232448 - 7168 - 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
+    // ring depth: what 227 KB leave next to my half of the query tile, the static arrays (~18.6 KB) and alignment
+    int n_stages = (232448 - 20480 - 1024 - n_kc * MM_CHUNK_BYTES) / MM_CHUNK_BYTES;
     if (n_stages > MM_MAX_STAGES) n_stages = MM_MAX_STAGES;
     const size_t smem = (size_t)(n_kc + n_stages) * MM_CHUNK_BYTES + 1024;
     CUtensorMap map_d, map_q;
