@@ -257,6 +257,56 @@ def run_c3_sharded(args):
     os._exit(0)
 
 
+def run_int8_sharded(args):
+    """Config 5 as named: the INT8 vectors doc-sharded over the ranks of this torchrun job, exhaustive scan with
+    fused top-100 per rank, NCCL all-gather of the candidates + merge kernel (dist.sharded_int8_scan)."""
+    import torch.distributed as dist
+    from b200ret.dist import shard_range, sharded_int8_scan
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=dev)
+    n, dim, k = args.docs, 768, args.k
+    lo, hi = shard_range(n, world, rank)
+    g = torch.Generator(device=dev); g.manual_seed(42 + 7919 * rank)
+    d8 = torch.randint(-127, 128, (hi - lo, dim), device=dev, dtype=torch.int8, generator=g)
+    ds = torch.rand(hi - lo, device=dev, generator=g) + 0.01
+    gq = torch.Generator(device=dev); gq.manual_seed(43)              # the same queries on every rank
+    for nq in args.queries:
+        q8 = torch.randint(-127, 128, (nq, dim), device=dev, dtype=torch.int8, generator=gq)
+        qs = (torch.rand(nq, device=dev, generator=gq) + 0.01) / 127
+        for _ in range(2):
+            sharded_int8_scan(q8, d8, qs, ds, k, lo)
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 5
+        a.record()
+        for _ in range(steps):
+            idx, val = sharded_int8_scan(q8, d8, qs, ds, k, lo)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # parity: the merged top-k of query 0 equals the top-k of the union of every rank's exact scores
+        dots = (d8.to(torch.int32) * q8[0].to(torch.int32)).sum(1).to(torch.float64)
+        sc = ((dots * qs[0].double()) * ds.double()).float()
+        loc = torch.topk(sc, k, sorted=True)
+        allv = [torch.empty_like(loc.values) for _ in range(world)]
+        dist.all_gather(allv, loc.values.contiguous())
+        want = torch.sort(torch.cat(allv), descending=True).values[:k]
+        if rank == 0:
+            ms_ = float(ms)
+            print(json.dumps({"config": f"c5: INT8 {dim}-d exhaustive scan, {n} vectors doc-sharded over {world} B200, "
+                                        f"top-{k}, NCCL all-gather + merge", "n_gpus": world, "queries": nq, "ms": ms_,
+                              "queries_per_s": nq / (ms_ * 1e-3), "int8_tops_all_gpus": 2.0 * nq * n * dim / (ms_ * 1e-3) / 1e12,
+                              "corpus_gbs_all_gpus": n * (dim + 4) / (ms_ * 1e-3) / 1e9,
+                              "top_values_match": bool(torch.equal(want, val[0]))}), flush=True)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", choices=["int8", "c3", "c4"])
@@ -274,6 +324,8 @@ def main():
         args.docs = {"int8": 2_000_000, "c3": 8_800_000, "c4": 2_200_000}[args.what]
     if args.what == "c3" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_c3_sharded(args)
+    elif args.what == "int8" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_int8_sharded(args)
     elif args.what == "int8":
         run_int8(args)
     else:
