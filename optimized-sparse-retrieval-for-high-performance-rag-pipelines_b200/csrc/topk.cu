@@ -12,6 +12,9 @@
 // Ranking rule and key layout: common.cuh.
 #include "common.cuh"
 
+#include <math.h>
+#include <stdlib.h>
+
 namespace b2r {
 
 constexpr int TK_THREADS = 256;
@@ -207,7 +210,16 @@ static TkPlan tk_plan(int64_t n_rows, int64_t n, int sub) {
     return p;
 }
 
-constexpr int TK_E_SCORES = 16;
+constexpr int TK_E_SCORES_DEFAULT = 16;
+// scores per thread and sub-chunk of the streaming selector: 16 or 32 (B2R_TOPK_E overrides: tuning experiments only)
+static int tk_e_scores() {
+    static const int v = [] {
+        const char *e = getenv("B2R_TOPK_E");
+        const int x = e ? atoi(e) : 0;
+        return x == 32 || x == 16 ? x : TK_E_SCORES_DEFAULT;
+    }();
+    return v;
+}
 constexpr int TK_E_KEYS = 8;
 
 static size_t tk_keys_ws(int64_t n_rows, int64_t n, int32_t k) {
@@ -223,7 +235,7 @@ static size_t tk_keys_ws(int64_t n_rows, int64_t n, int32_t k) {
 size_t topk_keys_ws_bytes(int64_t n_rows, int64_t n, int32_t k) { return tk_keys_ws(n_rows, n, k) + 256; }
 
 size_t topk_ws_bytes(int64_t n_rows, int64_t n, int32_t k) {
-    TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_SCORES);
+    TkPlan p = tk_plan(n_rows, n, TK_THREADS * tk_e_scores());
     if (p.n_segs == 1) return 256;
     size_t l1 = align_up((size_t)n_rows * p.n_segs * k * 8, 256);
     return l1 + tk_keys_ws(n_rows, (int64_t)p.n_segs * k, k) + 256;
@@ -270,7 +282,7 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
     B2R_CHECK_ARG(k >= 1 && k <= B2R_TOPK_MAX_FAST, "top-k: k=%d outside [1,%d]", k, B2R_TOPK_MAX_FAST);
     B2R_CHECK_ARG(doc_id_base >= 0 && doc_id_base + n < 0xFFFFFFFFll, "top-k: global doc index exceeds 2^32-2");
     B2R_CHECK_ARG(n_rows < 0x7FFFFFFFll, "top-k: too many rows");
-    TkPlan p = tk_plan(n_rows, n, TK_THREADS * TK_E_SCORES);
+    TkPlan p = tk_plan(n_rows, n, TK_THREADS * tk_e_scores());
     uint64_t *dst = keys_out;
     char *wp = static_cast<char *>(ws);
     size_t left = ws_bytes;
@@ -285,9 +297,15 @@ int topk_scores_rows(const float *scores, int64_t n_rows, int64_t n, int64_t row
         left -= need;
     }
     dim3 grid((unsigned)n_rows, (unsigned)p.n_segs);
-    topk_stream_kernel<false, TK_E_SCORES><<<grid, TK_THREADS, 0, st>>>(
-        scores, nullptr, n, row_stride, n, 0, (uint32_t)doc_id_base, k, p.seg_len, dst, opts.chunk_shift,
-        opts.chunk_stride, opts.gate, opts.gate_cap);
+    if (tk_e_scores() == 32) {
+        topk_stream_kernel<false, 32><<<grid, TK_THREADS, 0, st>>>(
+            scores, nullptr, n, row_stride, n, 0, (uint32_t)doc_id_base, k, p.seg_len, dst, opts.chunk_shift,
+            opts.chunk_stride, opts.gate, opts.gate_cap);
+    } else {
+        topk_stream_kernel<false, 16><<<grid, TK_THREADS, 0, st>>>(
+            scores, nullptr, n, row_stride, n, 0, (uint32_t)doc_id_base, k, p.seg_len, dst, opts.chunk_shift,
+            opts.chunk_stride, opts.gate, opts.gate_cap);
+    }
     B2R_LAUNCH_CHECK();
     if (p.n_segs == 1) return B2R_OK;
     int64_t n2 = (int64_t)p.n_segs * k;
@@ -453,6 +471,145 @@ int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t
     return B2R_OK;
 }
 
+// ------------------------------------------------------------------------------ threshold-filter top-k of score rows
+// The fast path of b2r_topk (fast_topk_selection) for long rows and k <= 128, the scheme of the fused search path
+// applied to a dense score matrix: (1) group maxima of every step-th 4096-score chunk, (2) the k-th largest group
+// maximum T per row (k groups, hence k scores, reach it), (3) one streaming pass that appends the scores >= T to a
+// candidate list (a quarter LDG.128 and one FMNMX per score, no barrier), (4) top-k of the lists.  Rows whose list
+// overflows (or comes up short: NaNs) are redone by the gated streaming selector.  Reads (1 + 1/step) x 4 B per score.
+constexpr int TF_CHUNK = 4096;  // scores per chunk = 256 threads x 4 x float4
+
+struct TfPlan {
+    bool on;
+    int step, cap;
+    int64_t n_chunks, n_sample, n_groups;
+};
+static TfPlan tf_plan(int64_t n, int32_t k) {
+    TfPlan p = {};
+    p.n_chunks = (n + TF_CHUNK - 1) / TF_CHUNK;
+    p.on = k >= 1 && k <= 128 && p.n_chunks >= 32;
+    if (!p.on) return p;
+    p.step = k <= 16 ? 64 : 16;
+    p.n_sample = (p.n_chunks + p.step - 1) / p.step;
+    p.n_groups = p.n_sample * 256;
+    const double r = (double)p.n_chunks / p.n_sample;
+    const double want = k * r + 6.0 * sqrt((double)k) * r + k;
+    p.cap = 256;
+    while (p.cap < want && p.cap < TL_MAX) p.cap <<= 1;
+    return p;
+}
+static size_t tf_bytes(const TfPlan &p, int64_t n_rows) {
+    if (!p.on) return 0;
+    return align_up((size_t)n_rows * p.n_groups * 4, 256) + align_up((size_t)n_rows * 8, 256) +
+           align_up((size_t)n_rows * p.cap * 8, 256) + align_up((size_t)n_rows * 4, 256) + 256;
+}
+
+// thread t of CTA (sample chunk j, row): maximum of its 16 scores of chunk j * step
+__global__ void __launch_bounds__(256)
+row_maxima_kernel(const float *__restrict__ scores, int64_t n, int64_t row_stride, int step, int64_t n_groups,
+                  float *__restrict__ maxima) {
+    const float *rp = scores + (int64_t)blockIdx.y * row_stride;
+    const int64_t base = (int64_t)blockIdx.x * step * TF_CHUNK;
+    float m = __int_as_float(0xff800000);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int64_t j = base + ((int64_t)v * 256 + threadIdx.x) * 4;
+        if (j + 3 < n) {
+            const float4 x = ldg_stream_f4(rp + j);
+            m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        } else {
+            for (int64_t e = j; e < n; ++e) m = fmaxf(m, __ldg(rp + e));
+        }
+    }
+    maxima[(int64_t)blockIdx.y * n_groups + (int64_t)blockIdx.x * 256 + threadIdx.x] = m;
+}
+
+// CTA (segment, row) walks chunks segment, segment + gridDim.x, ...; scores >= the row's threshold are keyed and appended
+__global__ void __launch_bounds__(256)
+row_filter_kernel(const float *__restrict__ scores, int64_t n, int64_t row_stride, int64_t n_chunks, uint32_t id_base,
+                  const uint64_t *__restrict__ thr_keys, uint64_t *__restrict__ cand, int32_t *__restrict__ cnt, int cap) {
+    const int row = blockIdx.y;
+    const float *rp = scores + (int64_t)row * row_stride;
+    const uint64_t thr = thr_keys[row];
+    const uint32_t thr_hi = (uint32_t)(thr >> 32);
+    const float thr_f = thr_hi ? unord_f32(thr_hi) : __int_as_float(0xff800000);
+    uint64_t *my = cand + (int64_t)row * cap;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int64_t base = c * TF_CHUNK + (int64_t)threadIdx.x * 4;
+        float4 x[4];
+        float m = __int_as_float(0xff800000);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int64_t j = base + (int64_t)v * 1024;
+            if (j + 3 < n) {
+                x[v] = ldg_stream_f4(rp + j);
+            } else {
+                const float ninf = __int_as_float(0xff800000);
+                x[v] = make_float4(j < n ? __ldg(rp + j) : ninf, j + 1 < n ? __ldg(rp + j + 1) : ninf,
+                                   j + 2 < n ? __ldg(rp + j + 2) : ninf, ninf);
+            }
+            m = fmaxf(m, fmaxf(fmaxf(x[v].x, x[v].y), fmaxf(x[v].z, x[v].w)));
+        }
+        if (m >= thr_f) {  // rare
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float f[4] = {x[v].x, x[v].y, x[v].z, x[v].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t j = base + (int64_t)v * 1024 + e;
+                    if (f[e] >= thr_f && j < n) {
+                        const uint64_t key = make_key(ord_f32(f[e]), id_base + (uint32_t)j);
+                        if (key > thr) {
+                            const int slot = atomicAdd(cnt + row, 1);
+                            if (slot < cap) my[slot] = key;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// keys_out[row, 0..k): exact top-k of every row through the threshold filter; rows it cannot finish fall back to
+// topk_scores_rows (gated).  Needs 16-byte aligned rows (checked by the caller).
+static int topk_scores_rows_filtered(const float *scores, int64_t n_rows, int64_t n, int64_t row_stride, int32_t k,
+                                     int64_t doc_id_base, uint64_t *keys_out, const TfPlan &p, void *ws,
+                                     size_t ws_bytes, cudaStream_t st) {
+    char *wp = static_cast<char *>(ws);
+    if (tf_bytes(p, n_rows) > ws_bytes) {
+        set_error("top-k: workspace too small (%zu > %zu)", tf_bytes(p, n_rows), ws_bytes);
+        return B2R_ERR_WORKSPACE;
+    }
+    auto carve = [&](size_t bytes) -> void * {
+        void *q = wp;
+        wp += align_up(bytes, 256);
+        return q;
+    };
+    float *maxima = static_cast<float *>(carve((size_t)n_rows * p.n_groups * 4));
+    uint64_t *thr = static_cast<uint64_t *>(carve((size_t)n_rows * 8));
+    uint64_t *cand = static_cast<uint64_t *>(carve((size_t)n_rows * p.cap * 8));
+    int32_t *cnt = static_cast<int32_t *>(carve((size_t)n_rows * 4));
+    const size_t left = ws_bytes - (size_t)(wp - static_cast<char *>(ws));
+    row_maxima_kernel<<<dim3((unsigned)p.n_sample, (unsigned)n_rows), 256, 0, st>>>(scores, n, row_stride, p.step,
+                                                                                  p.n_groups, maxima);
+    B2R_LAUNCH_CHECK();
+    int rc = kth_of_maxima(maxima, n_rows, p.n_groups, p.n_groups, k, false, false, thr, st);
+    if (rc) return rc;
+    B2R_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_rows * 4, st));
+    int64_t segs = (148 * 16 + n_rows - 1) / n_rows;
+    if (segs < 1) segs = 1;
+    if (segs > p.n_chunks) segs = p.n_chunks;
+    row_filter_kernel<<<dim3((unsigned)segs, (unsigned)n_rows), 256, 0, st>>>(scores, n, row_stride, p.n_chunks,
+                                                                            (uint32_t)doc_id_base, thr, cand, cnt, p.cap);
+    B2R_LAUNCH_CHECK();
+    rc = topk_of_lists(cand, n_rows, p.cap, cnt, k, k, keys_out, st);
+    if (rc) return rc;
+    TopkOpts gate;
+    gate.gate = cnt;
+    gate.gate_cap = p.cap;
+    return topk_scores_rows(scores, n_rows, n, row_stride, k, doc_id_base, keys_out, wp, left, st, gate);
+}
+
 // ------------------------------------------------------------------------------------------ decode
 __global__ void decode_keys_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t *__restrict__ idx_out,
                                    float *__restrict__ val_out, const float *__restrict__ scores,
@@ -526,10 +683,17 @@ static int full_sort_row(const float *scores, int64_t n, int64_t doc_id_base, ui
 
 using namespace b2r;
 
+// B2R_TOPK_FILTER=0 keeps b2r_topk on the streaming selector (A/B measurements only)
+static const bool g_topk_filter = [] {
+    const char *e = getenv("B2R_TOPK_FILTER");
+    return !(e && atoi(e) == 0);
+}();
+
 extern "C" int b2r_topk_workspace(int64_t n_rows, int64_t n, int32_t k, size_t *bytes) {
     B2R_CHECK_ARG(bytes && n_rows >= 0 && n >= 0 && k >= 1, "b2r_topk_workspace: bad arguments");
     if (k <= B2R_TOPK_MAX_FAST) {
-        *bytes = topk_ws_bytes(n_rows > 0 ? n_rows : 1, n > 0 ? n : 1, k) + (size_t)n_rows * k * 8 + 256;
+        *bytes = topk_ws_bytes(n_rows > 0 ? n_rows : 1, n > 0 ? n : 1, k) + (size_t)n_rows * k * 8 + 256 +
+                 tf_bytes(tf_plan(n > 0 ? n : 1, k), n_rows > 0 ? n_rows : 1);
     } else {
         *bytes = (size_t)pow2_ceil(n < 2 ? 2 : n) * 8 + 256;
     }
@@ -558,7 +722,11 @@ extern "C" int b2r_topk(const float *scores, int64_t n_rows, int64_t n, int64_t 
             wp += need;
             left -= need;
         }
-        int rc = topk_scores_rows(scores, n_rows, n, row_stride, k, doc_id_base, keys, wp, left, st);
+        const TfPlan fp = tf_plan(n, k);
+        const bool aligned = (reinterpret_cast<uintptr_t>(scores) & 15) == 0 && (n_rows == 1 || (row_stride & 3) == 0);
+        int rc = (fp.on && aligned && g_topk_filter)
+                     ? topk_scores_rows_filtered(scores, n_rows, n, row_stride, k, doc_id_base, keys, fp, wp, left, st)
+                     : topk_scores_rows(scores, n_rows, n, row_stride, k, doc_id_base, keys, wp, left, st);
         if (rc) return rc;
         return decode_keys(keys, n_rows * k, idx_out, val_out, scores, row_stride, k, doc_id_base, st);
     }

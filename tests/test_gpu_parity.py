@@ -301,6 +301,28 @@ def test_int8_pair_scan_equals_single_cta_and_oracle(b2r, nq, n):
             assert np.array_equal(_bits(pv[q].cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
 
 
+@pytest.mark.parametrize("rows,n,k", [(64, 300_000, 10), (33, 262_144 + 4, 100), (8, 1_000_000, 128), (5, 140_000, 1)])
+def test_topk_threshold_filter_path(b2r, rows, n, k):
+    """Long aligned rows with k <= 128 take the threshold-filter path of b2r_topk (group maxima -> k-th largest ->
+    one filtering pass -> top-k of the candidate lists); rows it cannot finish (massive ties at the threshold, NaN
+    rows, all-equal rows) must come out of the gated streaming selector with the same canonical result."""
+    rng = np.random.default_rng(111 + k)
+    s = rng.standard_normal((rows, n)).astype(np.float32)
+    s[1] = np.round(s[1] * 2) / 2                         # heavy ties everywhere
+    s[2, : n // 2] = np.nan                               # NaNs rank last
+    s[3] = 1.25                                           # all equal: lowest indices win
+    if rows > 4:
+        s[4, :] = -np.abs(s[4])
+        s[4, 100:100 + k] = 0.0                           # threshold exactly 0, zeros tie with -0.0
+        s[4, 7] = -0.0
+    idx, val = b2r.fast_topk_selection(torch.from_numpy(s).cuda(), k)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for r in range(rows):
+        wi, wv = np_oracle.topk_canonical(s[r], k)
+        assert np.array_equal(idx[r], wi), r
+        assert np.array_equal(_bits(val[r]), _bits(s[r][wi])), r
+
+
 # ----------------------------------------------------------------------------------- golden + edge: K2
 def test_topk_reference_cases(b2r, golden_dir):
     z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
