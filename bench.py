@@ -89,7 +89,7 @@ def run_reference(args):
         return 0
     from oracle import c_oracle
     w = make_workload(args.workload, args.n_queries)
-    cores = c_oracle.num_threads()
+    cores = c_oracle.use_all_host_threads()
     # size the per-step sample so that a step takes ~1.5 s
     rate, dt = cpu_reference_rate(w, 2)
     n_sample = int(max(2, min(len(w["q_ptr"]) - 1, round(1.5 * rate))))
@@ -367,10 +367,11 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import c_oracle
+            cores = c_oracle.use_all_host_threads()
             r2, _ = cpu_reference_rate(w, 2)
             n_sample = int(max(2, min(nq, round(12.0 * r2))))
             rate, dt = cpu_reference_rate(w, n_sample)
-            out["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": c_oracle.num_threads(), "kind": "port",
+            out["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
                                    "sample": f"first {n_sample} of {nq} queries, full corpus, {dt:.1f} s of wall time"}
         emit(out)
     if world > 1:

@@ -40,6 +40,18 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def use_all_host_threads() -> int:
+    """bench.py's CPU legs: use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it
+    to 1 for every rank).  Returns the thread count in effect."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:      # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 def bm25_scores(query_tf, data, indices, indptr, doc_lengths, idf, k1, b, avgdl):
     query_tf = np.ascontiguousarray(query_tf, np.float32)
     data = np.ascontiguousarray(data, np.float32)
