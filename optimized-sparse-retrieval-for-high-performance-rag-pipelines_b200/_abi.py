@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ret.so")
+# B2R_LIB_PATH: load another build of the same library (same-box A/B measurements of two kernel variants)
+LIB_PATH = os.environ.get("B2R_LIB_PATH") or os.path.join(_HERE, "libb200ret.so")
 
 OK = 0
 KIND_BM25 = 0
