@@ -65,7 +65,7 @@ __device__ __forceinline__ void sc_mbar_wait(uint32_t bar, uint32_t parity) {
 // `0.0 + x` is still evaluated so that the stored bits are those of the reference's `acc += x`.
 template <int KIND, bool FIRST>
 __device__ __forceinline__ void apply_posting(double *acc_w, uint32_t rel, double u_or_w, float w_idf, float w_q,
-                                              double w_idf64, double w_q64) {
+                                              double w_idf64, double w_q64) {  // BM25 uses the doubles, IMPACT the floats
     const double a = FIRST ? 0.0 : acc_w[rel];
     if (KIND == B2R_KIND_BM25) {
         acc_w[rel] = __dadd_rn(a, __dmul_rn(__dmul_rn(w_idf64, u_or_w), w_q64));
@@ -82,13 +82,32 @@ __device__ __forceinline__ double load_val(const void *post_val, uint32_t p) {
     return (double)ld_stream_f32(static_cast<const float *>(post_val) + p);
 }
 
+// type in which a staged term's idf and query weight travel between lanes
+template <int KIND>
+struct TermW {
+    using type = float;
+};
+#ifndef SC_WT64
+#define SC_WT64 0  // 1: BM25 term weights are widened to f64 once per lane at staging (needs > 40 registers: spills at 6 CTAs/SM)
+#endif
+#if SC_WT64
+template <>
+struct TermW<B2R_KIND_BM25> {
+    using type = double;
+};
+#endif
+
 // One term applied by one warp to its own sub-tile.  dense: [beg, end) are exactly the warp's postings;
 // otherwise [beg, end) is the tile's (small) block and the warp keeps the postings of its doc range.
 template <int KIND, bool FIRST>
 __device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end, int lane, int sub, uint32_t my_doc0,
                                            const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
-                                           double *acc_w, float w_idf, float w_q) {
-    const double w_idf64 = (double)w_idf, w_q64 = (double)w_q;
+                                           double *acc_w, typename TermW<KIND>::type w_idf_t,
+                                           typename TermW<KIND>::type w_q_t) {
+    // BM25 multiplies in f64: the widening was done ONCE per lane when the query was staged (f32 -> f64 conversions
+    // run on a slow pipe, and this function is entered once per term, warp and tile)
+    const double w_idf64 = (double)w_idf_t, w_q64 = (double)w_q_t;
+    const float w_idf = (float)w_idf_t, w_q = (float)w_q_t;  // (exact: the values are f32 numbers)
     if (dense) {
         uint32_t p = beg + lane;
         for (; p + 96 < end; p += 128) {  // 4 independent postings in flight per lane
@@ -143,7 +162,10 @@ struct ScoreOut {
 };
 
 template <int KIND, int OUT>
-__global__ void __launch_bounds__(SC_THREADS, 6)  // 6 CTAs/SM is what 32 KB of accumulators per CTA allows
+#ifndef SC_MIN_CTAS
+#define SC_MIN_CTAS 6  // 6 CTAs/SM is what 32 KB of accumulators per CTA allows (40 registers per thread)
+#endif
+__global__ void __launch_bounds__(SC_THREADS, SC_MIN_CTAS)
 score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
                    const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
                    const uint32_t *__restrict__ dense_ptr, int n_tiles, int tile_docs,
@@ -177,7 +199,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     // per CTA instead of once per tile.
     const bool staged = qe - qs <= 32;
     const uint32_t *my_row = nullptr;  // dense: offsets per sub-tile; sparse: offsets per tile
-    float my_idf = 0.f, my_qw = 0.f;
+    typename TermW<KIND>::type my_idf = 0, my_qw = 0;
     int my_dense = 0;
     uint32_t nxt_beg = 0, nxt_end = 0;
     if (staged && lane < qe - qs) {
@@ -246,7 +268,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
             if (beg == end) continue;  // warp-uniform
             const int dense = __shfl_sync(full, my_dense, j);
-            const float w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
+            const typename TermW<KIND>::type w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
             if (first) apply_term<KIND, true>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
             else apply_term<KIND, false>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
             first = false;
