@@ -116,8 +116,11 @@ extern "C" int b2r_f32_dot_topk(const float *emb, int64_t n_rows, int32_t dim, c
     const int dim4 = (dim + 3) & ~3;
     int64_t blocks = (n_rows * 32 + DN_THREADS - 1) / DN_THREADS;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    for (int q0 = 0; q0 < n_q; q0 += DN_QC) {
-        const int nq = n_q - q0 < DN_QC ? n_q - q0 : DN_QC;
+    // queries per pass: 8, fewer when their vectors would not fit 192 KB of shared memory (very wide embeddings)
+    int qc = (int)(196608 / ((size_t)dim4 * 4));
+    qc = qc < 1 ? 1 : (qc > DN_QC ? DN_QC : qc);
+    for (int q0 = 0; q0 < n_q; q0 += qc) {
+        const int nq = n_q - q0 < qc ? n_q - q0 : qc;
         const size_t smem = (size_t)nq * dim4 * 4;
         B2R_CUDA(cudaFuncSetAttribute(f32_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         f32_dot_kernel<<<(unsigned)blocks, DN_THREADS, smem, st>>>(emb, n_rows, dim, queries, q0, nq, scores, stride);

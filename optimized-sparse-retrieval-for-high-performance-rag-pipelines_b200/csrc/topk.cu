@@ -407,7 +407,8 @@ topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__res
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
                   uint64_t *keys_out, cudaStream_t st) {
     if (n_rows == 0) return B2R_OK;
-    B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap, "top-k of lists: cap=%d / k=%d unsupported", cap, k);
+    B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap && k <= B2R_TOPK_MAX_FAST,
+                  "top-k of lists: cap=%d / k=%d unsupported", cap, k);
     topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, 0, st>>>(lists, cap, cnt, k, min_cnt, keys_out);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
