@@ -272,13 +272,14 @@ def test_service_search_by_vector(b2r, tmp_path):
     assert len(svc.search_by_vector(emb[17], k=5, min_score=cut - 1e-4)) == 3
 
 
-@pytest.mark.parametrize("nq,n", [(130, 70_000 + 13), (512, 40_000), (257, 33_000 + 129)])
-def test_int8_pair_scan_equals_single_cta_and_oracle(b2r, nq, n):
+@pytest.mark.parametrize("nq,n,dim", [(130, 70_000 + 13, 768), (512, 40_000, 768), (257, 33_000 + 129, 768),
+                                      (300, 36_000, 128), (200, 34_000 + 7, 384)])
+def test_int8_pair_scan_equals_single_cta_and_oracle(b2r, nq, n, dim):
     """CTA-pair fused scan (tcgen05.mma cta_group::2, 256 x 256 pair tiles) vs the single-CTA fused scan vs exact
     integer math: odd query counts (zero-padded operand halves), an odd number of 128-document tiles (the second
     CTA of the last pair sees only padding), overflowing candidate lists."""
     rng = np.random.default_rng(101 + nq)
-    dim, k = 768, 100
+    k = 100
     q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
     d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
     qs = (rng.random(nq).astype(np.float32) + 0.01) / 127
