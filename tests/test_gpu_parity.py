@@ -324,6 +324,41 @@ def test_topk_threshold_filter_path(b2r, rows, n, k):
         assert np.array_equal(_bits(val[r]), _bits(s[r][wi])), r
 
 
+def test_int8_dense_epilogue_exact_on_ties_and_at_scale(b2r):
+    """quantized_dot_product_batch must return f32((f64(dot) * f64(qs)) * f64(ds)) bit for bit whatever the
+    epilogue does internally (a conversion-free f32 evaluation with an f64 fallback near ties was measured in round 1
+    and passed this test, but was slower than the plain f64 chain and is not in the library).  (1) crafted exact ties:
+    odd dots in [2^23/1.5, 2^24/1.5) with qs = 1, ds = 1.5 put dot * 1.5 exactly half-way between two f32 numbers
+    (round-to-even must win), plus powers of two, zero dots with signed scales, extreme scales; (2) 25 M random
+    outputs against an exact f64 evaluation."""
+    dim = 768
+    q = np.zeros((4, dim), np.int8); q[:, :600] = 127; q[:, 600:664] = 1
+    q[1] = -q[1]; q[2] = 0; q[3, :] = 0; q[3, 0] = 64
+    n = 400
+    d = np.zeros((n, dim), np.int8); d[:, :600] = 127                    # 127 * 127 * 600 = 9,677,400 (even)
+    rng = np.random.default_rng(5)
+    d[:, 600:664] = rng.integers(-127, 128, (n, 64))                      # dot = 9,677,400 + sum: odd half of the time
+    d[7] = 0; d[8] = 0; d[8, 0] = 64                                      # dot 0 and 4096 (a power of two) with q[3]
+    qs = np.array([1.0, 1.0, 0.25, 1.0], np.float32)
+    ds = np.full(n, 1.5, np.float32)
+    ds[1::4] = -1.5; ds[2::8] = 3e-13; ds[3::8] = 7e13; ds[5] = 0.0; ds[6] = 0.75
+    got = b2r.quantized_dot_product_batch(q, d, qs, ds)
+    want = np_oracle.int8_dot_batch(q, d, qs, ds)
+    assert np.array_equal(_bits(got), _bits(want))
+    dots = q.astype(np.int64) @ d.astype(np.int64).T
+    assert (np.abs(dots[0]) % 2 == 1).sum() > 50                          # the exact ties are really there
+    rng = np.random.default_rng(6)
+    nq, n2 = 256, 100_000
+    q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+    d8 = rng.integers(-127, 128, (n2, dim)).astype(np.int8)
+    qs2 = ((rng.random(nq) + 0.01) / 127).astype(np.float32)
+    ds2 = (rng.random(n2) + 0.01).astype(np.float32)
+    got = b2r.quantized_dot_product_batch(q8, d8, qs2, ds2)
+    dd = q8.astype(np.float64) @ d8.astype(np.float64).T                  # exact: |dot| < 2^24
+    want = ((dd * qs2.astype(np.float64)[:, None]) * ds2.astype(np.float64)[None, :]).astype(np.float32)
+    assert np.array_equal(_bits(got), _bits(want))
+
+
 # ----------------------------------------------------------------------------------- golden + edge: K2
 def test_topk_reference_cases(b2r, golden_dir):
     z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
