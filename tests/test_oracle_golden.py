@@ -151,3 +151,34 @@ def test_service_text_matches_reference(golden_dir):
         assert got500[qid].keys() == ref.keys()
         for d, v in ref.items():
             assert got500[qid][d] == v
+
+
+def test_hybrid_rerank_restatement_is_consistent_with_the_pinned_pieces():
+    """np_oracle.hybrid_rerank (the fusion rule has no reference implementation to pin it to) must at least agree
+    with the pinned pieces it is made of: dense part == int8_dot_batch restricted to the candidates, selection ==
+    topk_canonical on the fused scores, padding and shard windows as documented."""
+    rng = np.random.default_rng(3)
+    nq, n, dim, k_in, k_out, base = 5, 300, 48, 20, 6, 1000
+    q8 = rng.integers(-127, 128, (nq, dim)).astype(np.int8)
+    d8 = rng.integers(-127, 128, (n, dim)).astype(np.int8)
+    qs = (rng.random(nq).astype(np.float32) + 0.01) / 127
+    ds = rng.random(n).astype(np.float32) + 0.01
+    cand = np.stack([rng.choice(n, k_in, replace=False) for _ in range(nq)]).astype(np.int64) + base
+    cand[0, 3] = -1
+    cand[1, 5] = base + n            # outside the shard
+    cand[2, :] = -1                  # nothing to rerank
+    sparse = (rng.random((nq, k_in)) * 10).astype(np.float32)
+    full = np_oracle.int8_dot_batch(q8, d8, qs, ds)
+    for sp in (sparse, None):
+        idx, val, dense = np_oracle.hybrid_rerank(cand, sp, q8, qs, d8, ds, 0.3, 0.7, k_out, doc_id_base=base)
+        assert idx.shape == (nq, k_out) and val.shape == (nq, k_out) and dense.shape == (nq, k_in)
+        assert (idx[2] == -1).all() and np.isneginf(val[2]).all() and np.isneginf(dense[2]).all()
+        for q in (0, 1, 3, 4):
+            ok = (cand[q] >= base) & (cand[q] < base + n)
+            assert np.array_equal(dense[q, ok], full[q, cand[q, ok] - base]) and np.isneginf(dense[q, ~ok]).all()
+            fused = dense[q, ok] if sp is None else (
+                np.float64(np.float32(0.3)) * sp[q, ok].astype(np.float64)
+                + np.float64(np.float32(0.7)) * dense[q, ok].astype(np.float64)).astype(np.float32)
+            order = np.lexsort((cand[q, ok], -fused))[:k_out]
+            assert np.array_equal(idx[q, :len(order)], cand[q, ok][order])
+            assert np.array_equal(val[q, :len(order)], fused[order])
