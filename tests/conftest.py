@@ -11,6 +11,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # The shared libraries are build artefacts (git-ignored): in a fresh checkout compile them once, exactly as
+    # __graft_entry__.build() does (nvcc cross-compiles sm_100a without a GPU), so that the suite never runs
+    # against a missing or silently absent product library.
+    pkg = os.path.join(ROOT, "optimized-sparse-retrieval-for-high-performance-rag-pipelines_b200")
+    if not os.path.exists(os.path.join(pkg, "libb200ret.so")) or \
+            not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(pkg, "csrc")], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
 
 
 def pytest_collection_modifyitems(config, items):
