@@ -158,6 +158,23 @@ class MemoryIndex:
     def get_document_count(self) -> int:
         return len(self._where)
 
+    def get_document_ids(self) -> List[str]:
+        """memory_index.py:474-476."""
+        return list(self._where.keys())
+
+    def contains(self, doc_id: str) -> bool:
+        """memory_index.py:478-480."""
+        return doc_id in self._where
+
+    def get_index_stats(self) -> Dict[str, object]:
+        """memory_index.py:482-499 (same keys; there is no LRU cache in this shim, so its stats are empty)."""
+        size = self.index_path.stat().st_size if self.index_path.exists() else 0
+        n = len(self._where)
+        return {"num_documents": n, "file_size_mb": size / (1024 * 1024),
+                "average_doc_size_bytes": (size - _FILE_HDR.size) / n if n else 0,
+                "cache_stats": {"size": 0, "capacity": self.cache_size}, "compression_enabled": True,
+                "memory_mapped": self._map is not None}
+
     def __contains__(self, doc_id: str) -> bool:
         return doc_id in self._where
 

@@ -147,6 +147,11 @@ def test_docstore_roundtrip(tmp_path):
     assert d.text == docs[3].text and d.title == "T3" and d.metadata == {"i": 3}
     assert ix.get_document("nope") is None
     assert [x.id for x in ix.get_documents(["d6", "d0"])] == ["d6", "d0"]
+    assert ix.get_document_ids() == [f"d{i}" for i in range(7)] and ix.contains("d2") and not ix.contains("zz")
+    st = ix.get_index_stats()                                   # keys of memory_index.py:482-499
+    assert sorted(st) == ["average_doc_size_bytes", "cache_stats", "compression_enabled", "file_size_mb",
+                          "memory_mapped", "num_documents"]
+    assert st["num_documents"] == 7 and st["memory_mapped"] and st["file_size_mb"] > 0
     ix.close()
 
 
