@@ -222,3 +222,15 @@ def test_sharded_plumbing_gloo_world2(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_product_quantisers_match_the_reference_outputs(golden_dir):
+    """b200ret.synthetic.quantize_corpus mirrors _quantize_embeddings (retriever_registry.py:435-447): checked against
+    the int8 codes / scales the reference itself produced (tests/golden/int8.npz, written by oracle/gen_golden.py)."""
+    from b200ret import synthetic as S
+    z = np.load(os.path.join(golden_dir, "int8.npz"))
+    q, sc = S.quantize_corpus(z["emb"])
+    assert q.dtype == np.int8 and sc.dtype == np.float32
+    assert np.array_equal(q, z["d8"][:len(q)]) and np.array_equal(sc, z["dscale"][:len(q)])
+    q2, s2 = S.quantize_queries(z["emb"][:4])
+    assert q2.dtype == np.int8 and np.abs(q2).max() == 127 and np.allclose(q2 * s2[:, None], z["emb"][:4], atol=s2.max())
