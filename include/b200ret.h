@@ -242,7 +242,7 @@ int b2r_int8_scan_topk(const int8_t *q8, int32_t n_q, const int8_t *d8, int64_t 
 int b2r_int8_rerank_workspace(int32_t n_q, int32_t k_in, int32_t k_out, size_t *bytes);
 int b2r_int8_rerank(const int64_t *cand_idx, const float *cand_sparse, int32_t n_q, int32_t k_in, const int8_t *q8,
                     const float *q_scale, const int8_t *d8, const float *d_scale, int64_t n_docs, int32_t dim,
-                    int64_t doc_id_base, float sparse_weight, float dense_weight, int32_t k_out, float *dense_out,
+                    int64_t doc_id_base, double sparse_weight, double dense_weight, int32_t k_out, float *dense_out,
                     int64_t *idx_out, float *val_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* fp32 dense similarity + top-k: scores[q, r] = <emb[r, :], queries[q, :]> over a row-major f32[n_rows, dim]

@@ -117,7 +117,7 @@ SIGNATURES = {
     "b2r_f32_dot_topk_workspace": (C.c_int, [_I32, _I64, _I32, C.POINTER(_SZ)]),
     "b2r_f32_dot_topk": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _I64, _P, _I64, _P, _P, _P, _SZ, _P]),
     "b2r_int8_rerank_workspace": (C.c_int, [_I32, _I32, _I32, C.POINTER(_SZ)]),
-    "b2r_int8_rerank": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _I64, C.c_float, C.c_float, _I32, _P, _P,
+    "b2r_int8_rerank": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _I64, _F64, _F64, _I32, _P, _P,
                                   _P, _P, _SZ, _P]),
     "b2r_int8_scan_topk": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _P, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
 }

@@ -17,4 +17,6 @@ void set_error(const char *fmt, ...) {
 
 extern "C" int b2r_version(void) { return B2R_VERSION; }
 extern "C" const char *b2r_last_error(void) { return b2r::g_err; }
-extern "C" unsigned long long b2r_launch_count(void) { return b2r::g_launches; }
+extern "C" unsigned long long b2r_launch_count(void) {
+    return __atomic_load_n(&b2r::g_launches, __ATOMIC_RELAXED);
+}

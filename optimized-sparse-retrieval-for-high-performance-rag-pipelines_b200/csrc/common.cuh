@@ -29,11 +29,12 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 // every kernel launch of the library goes through this macro; the counter backs b2r_launch_count()
+// (relaxed atomic: searches may be enqueued from several host threads)
 extern unsigned long long g_launches;
-#define B2R_LAUNCH_CHECK()               \
-    do {                                 \
-        ++b2r::g_launches;               \
-        B2R_CUDA(cudaGetLastError());    \
+#define B2R_LAUNCH_CHECK()                                                \
+    do {                                                                  \
+        __atomic_fetch_add(&b2r::g_launches, 1ull, __ATOMIC_RELAXED);     \
+        B2R_CUDA(cudaGetLastError());                                     \
     } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

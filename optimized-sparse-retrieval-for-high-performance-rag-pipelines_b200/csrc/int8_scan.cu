@@ -528,9 +528,10 @@ int8_mma_kernel(const __grid_constant__ CUtensorMap map_d, const __grid_constant
     }
 }
 
+// the ONE shape predicate of the tcgen05 path: b2r_int8_scan_workspace (no pointers yet) and the call path share it
+static bool mma_dim_ok(int dim) { return dim % MM_KC == 0 && dim / MM_KC >= 1 && dim / MM_KC <= MM_MAX_KC; }
 static bool mma_shape_ok(int dim, const void *q8, const void *d8) {
-    return dim % MM_KC == 0 && dim / MM_KC >= 1 && dim / MM_KC <= MM_MAX_KC &&
-           (reinterpret_cast<uintptr_t>(q8) & 15) == 0 && (reinterpret_cast<uintptr_t>(d8) & 15) == 0;
+    return mma_dim_ok(dim) && (reinterpret_cast<uintptr_t>(q8) & 15) == 0 && (reinterpret_cast<uintptr_t>(d8) & 15) == 0;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -895,6 +896,8 @@ static int launch_int8_mma(const int8_t *q8, int n_q, const int8_t *d8, int64_t 
     int64_t gy = (int64_t)max_clusters / (gx / csize);
     if (gy < 1) gy = 1;
     if (gy > n_logical) gy = n_logical;
+    // the MAXIMA epilogue writes maxima[n_q][MM_MAX_GROUPS]: one row of MM_M maxima per CTA row y
+    if (gy > MM_MAX_GROUPS / MM_M) gy = MM_MAX_GROUPS / MM_M;
     cfg.gridDim = dim3((unsigned)gx, (unsigned)gy);
     if (gy_out) *gy_out = (int)gy;
     static const int diag = [] {
@@ -1056,8 +1059,8 @@ extern "C" int b2r_int8_scan_workspace(int32_t n_q, int64_t n_docs, int32_t dim,
     int64_t nq = n_q > 0 ? n_q : 1;
     int64_t chunk = i8_chunk_docs(n_q, n_docs);
     int64_t n_chunks = (n_docs + chunk - 1) / chunk;
-    const bool shape_ok = dim % MM_KC == 0 && dim / MM_KC >= 1 && dim / MM_KC <= MM_MAX_KC;
-    const I8Fused fp = i8_fused_plan(n_q, n_docs, dim, k, shape_ok);
+    // (a misaligned q8 / d8 pointer later turns the fused path off: the workspace is then merely larger than needed)
+    const I8Fused fp = i8_fused_plan(n_q, n_docs, dim, k, mma_dim_ok(dim));
     *bytes = align_up((size_t)nq * chunk * 4, 256) + topk_ws_bytes(nq, chunk, k) +
              align_up((size_t)n_chunks * nq * k * 8, 256) + topk_keys_ws_bytes(nq, n_chunks * k, k) +
              align_up((size_t)nq * k * 8, 256) + i8_fused_bytes(fp, nq, k) + 1024;

@@ -85,8 +85,8 @@ extern "C" int b2r_int8_rerank_workspace(int32_t n_q, int32_t k_in, int32_t k_ou
 
 extern "C" int b2r_int8_rerank(const int64_t *cand_idx, const float *cand_sparse, int32_t n_q, int32_t k_in,
                                const int8_t *q8, const float *q_scale, const int8_t *d8, const float *d_scale,
-                               int64_t n_docs, int32_t dim, int64_t doc_id_base, float sparse_weight,
-                               float dense_weight, int32_t k_out, float *dense_out, int64_t *idx_out, float *val_out,
+                               int64_t n_docs, int32_t dim, int64_t doc_id_base, double sparse_weight,
+                               double dense_weight, int32_t k_out, float *dense_out, int64_t *idx_out, float *val_out,
                                void *workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B2R_CHECK_ARG(cand_idx && q8 && q_scale && d8 && d_scale && n_q >= 0 && k_in >= 1 && n_docs >= 1 && dim >= 1,
@@ -111,7 +111,7 @@ extern "C" int b2r_int8_rerank(const int64_t *cand_idx, const float *cand_sparse
     dim3 grid((unsigned)((k_in + 63) / 64), (unsigned)n_q);
     const size_t smem = (size_t)((dim + 15) & ~15);
     rerank_kernel<<<grid, RR_THREADS, smem, st>>>(cand_idx, cand_sparse, k_in, q8, q_scale, d8, d_scale, n_docs, dim,
-                                                  doc_id_base, (double)sparse_weight, (double)dense_weight, dense_out,
+                                                  doc_id_base, sparse_weight, dense_weight, dense_out,
                                                   keys);
     B2R_LAUNCH_CHECK();
     int rc = topk_keys_rows(keys, n_q, k_in, k_in, k_in, 0, k_out, best, wp, left, st);

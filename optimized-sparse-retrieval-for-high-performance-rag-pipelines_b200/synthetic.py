@@ -10,7 +10,7 @@ from typing import Tuple
 import numpy as np
 
 __all__ = ["zipf_corpus", "zipf_queries", "impact_corpus", "impact_queries", "clustered_embeddings",
-           "quantize_corpus", "quantize_queries"]
+           "quantize_corpus", "quantize_queries", "fiqa_shape_corpus", "fiqa_shape_queries", "FIQA_SHAPE"]
 
 
 def _zipf_cdf(n: int) -> np.ndarray:
@@ -137,3 +137,60 @@ def quantize_queries(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     scales = (np.max(np.abs(x), axis=1) / 127.0).astype(np.float32)
     scales = np.where(scales == 0, np.float32(1.0), scales)
     return np.clip(np.round(x / scales[:, None]), -127, 127).astype(np.int8), scales
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 1: the FiQA-shape TEXT corpus of the reference's own generator
+# (tests/core_test.py:203-252, SyntheticDataGenerator: seeds 42 / 43).  The reference draws
+# `np.random.choice(vocab, size=L, p=zipf)` per document after `np.random.seed(seed)`; the legacy
+# RandomState stream is frozen across numpy versions, and choice-with-p is `cdf.searchsorted(
+# random_sample(L), side="right")` on the normalised cumulative sum, so the generator below produces
+# the same texts word for word (oracle/gen_golden.py checks the sha256 of both) at a fifth of the cost.
+FIQA_SHAPE = dict(num_docs=57_638, avg_doc_length=132, vocab_size=60_000, corpus_seed=42,
+                  num_queries=648, avg_query_length=11, query_seed=43)
+
+
+def _legacy_zipf_cdf(n: int) -> np.ndarray:
+    p = 1.0 / np.arange(1, n + 1)
+    p /= p.sum()
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    return cdf
+
+
+def fiqa_shape_corpus(num_docs: int = FIQA_SHAPE["num_docs"], avg_doc_length: int = FIQA_SHAPE["avg_doc_length"],
+                      vocab_size: int = FIQA_SHAPE["vocab_size"], seed: int = FIQA_SHAPE["corpus_seed"]):
+    """Dict doc_id -> {"text", "title"} identical to SyntheticDataGenerator.generate_corpus (core_test.py:206-228)."""
+    rs = np.random.RandomState(seed)
+    cdf = _legacy_zipf_cdf(vocab_size)
+    corpus = {}
+    for d in range(num_docs):
+        length = max(10, int(rs.gamma(2, avg_doc_length / 2)))
+        ids = cdf.searchsorted(rs.random_sample(length), side="right")
+        corpus[f"doc_{d}"] = {"text": " ".join([f"word_{w}" for w in ids]), "title": f"Document {d}"}
+    return corpus
+
+
+def fiqa_shape_queries(num_queries: int = FIQA_SHAPE["num_queries"], avg_query_length: int = FIQA_SHAPE["avg_query_length"],
+                       vocab_size: int = FIQA_SHAPE["vocab_size"], seed: int = FIQA_SHAPE["query_seed"]):
+    """Dict qid -> text identical to SyntheticDataGenerator.generate_queries (core_test.py:230-252)."""
+    rs = np.random.RandomState(seed)
+    cdf = _legacy_zipf_cdf(vocab_size // 10)
+    queries = {}
+    for q in range(num_queries):
+        length = max(1, int(rs.gamma(1.5, avg_query_length / 1.5)))
+        ids = cdf.searchsorted(rs.random_sample(length), side="right")
+        queries[f"query_{q}"] = " ".join([f"word_{w}" for w in ids])
+    return queries
+
+
+def corpus_sha256(corpus) -> str:
+    """sha256 over "<doc_id>\t<text>\n" of every document in insertion order (pins a generated text corpus)."""
+    import hashlib
+    h = hashlib.sha256()
+    for doc_id, doc in corpus.items():
+        h.update(doc_id.encode())
+        h.update(b"\t")
+        h.update(doc.get("text", "").encode())
+        h.update(b"\n")
+    return h.hexdigest()

@@ -208,8 +208,85 @@ def main():
     with open(os.path.join(OUT, "service_text.json"), "w") as f:
         json.dump(dict(corpus=corpus, queries=queries, ref_top10=res10, ref_top500=res500, meta=meta,
                        versions=versions), f)
+    fiqa_shape(ref_ret, versions)
     print("golden fixtures written to", OUT, versions)
 
 
+def fiqa_shape(ref_ret, versions):
+    """BASELINE config 1: the reference's RetrievalService on the FiQA-shape synthetic text corpus of its own
+    generator (tests/core_test.py:203-252; 57,638 docs, 648 queries, top-10).  The corpus (68 MB of text) is not
+    committed: the fixture pins it by sha256 and the product-side generator (b200ret/synthetic.py, loaded here
+    without the CUDA library) is checked to reproduce the reference generator's output exactly.  Stored per query:
+    what search_bm25 returned, and the canonical top-10 (score desc, doc index asc) of the reference's OWN score
+    vector (simd_bm25_score called exactly as _score_bm25_query does), which is what a deterministic tie rule must
+    reproduce."""
+    import importlib.util
+    import re as _re
+    from collections import Counter
+    sys.path.insert(0, os.path.join(REF, "tests"))
+    from core_test import SyntheticDataGenerator
+    from rag_system.core.memory_index import MemoryIndex
+    spec = importlib.util.spec_from_file_location(
+        "b2r_synthetic", os.path.join(os.path.dirname(HERE), "optimized-sparse-retrieval-for-high-performance-rag-pipelines_b200",
+                                      "synthetic.py"))
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    cfg = syn.FIQA_SHAPE
+    corpus = {}
+    for d in SyntheticDataGenerator.generate_corpus(cfg["num_docs"], cfg["avg_doc_length"], cfg["vocab_size"],
+                                                    seed=cfg["corpus_seed"]):
+        corpus[d["_id"]] = {"text": d["text"], "title": d["title"]}
+    queries = {q["qid"]: q["text"] for q in SyntheticDataGenerator.generate_queries(
+        cfg["num_queries"], cfg["avg_query_length"], cfg["vocab_size"], seed=cfg["query_seed"])}
+    sha = syn.corpus_sha256(corpus)
+    mine = syn.fiqa_shape_corpus()
+    assert syn.corpus_sha256(mine) == sha and list(mine) == list(corpus), "restated corpus generator diverges"
+    assert syn.fiqa_shape_queries() == queries, "restated query generator diverges"
+    del mine
+    k = 10
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "docs.idx")
+        MemoryIndex(path, create=True)
+        svc = ref_ret.RetrievalService(path)
+        svc.build_bm25_index(corpus)
+        res = svc.search_bm25(queries, top_k=k)
+        nq = len(queries)
+        ref_idx = np.full((nq, k), -1, np.int64)
+        ref_val = np.zeros((nq, k), np.float32)
+        canon_idx = np.full((nq, k), -1, np.int64)
+        canon_val = np.zeros((nq, k), np.float32)
+        pos = {d: i for i, d in enumerate(svc.doc_ids)}
+        for qi, (qid, text) in enumerate(queries.items()):
+            for j, (doc_id, sc) in enumerate(res[qid].items()):
+                ref_idx[qi, j], ref_val[qi, j] = pos[doc_id], np.float32(sc)
+            counts = Counter(_re.findall(r"\b\w+\b", text.lower()))
+            qtf = np.zeros(len(svc.vocabulary), np.float32)
+            hit = 0
+            for t, c in counts.items():
+                if t in svc.vocabulary:
+                    qtf[svc.vocabulary[t]] = float(c)
+                    hit += 1
+            if not hit:
+                continue
+            s = ref_ret.simd_bm25_score(qtf, svc.corpus_tf.data, svc.corpus_tf.indices, svc.corpus_tf.indptr,
+                                        svc.doc_lengths, svc.idf_weights, svc.k1, svc.b, svc.avgdl)
+            ci, cv = np_oracle.topk_canonical(s, k)
+            canon_idx[qi, :len(ci)], canon_val[qi, :len(ci)] = ci, cv
+        meta = dict(corpus_sha256=sha, n_docs=len(svc.doc_ids), vocab_size=len(svc.vocabulary),
+                    nnz=int(svc.corpus_tf.nnz), avgdl=svc.avgdl,
+                    idf_sum=float(np.sum(svc.idf_weights.astype(np.float64))),
+                    n_empty_results=int(sum(1 for r in res.values() if not r)), versions=versions, config=cfg)
+        svc.close()
+    np.savez_compressed(os.path.join(OUT, "fiqa_shape.npz"), ref_idx=ref_idx, ref_val=ref_val, canon_idx=canon_idx,
+                        canon_val=canon_val, meta=np.asarray(json.dumps(meta)))
+    print("fiqa-shape fixture:", meta)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fiqa":      # only the (slow) config-1 fixture
+        import numba, scipy
+        from rag_system.core import retrieval as _ref_ret
+        fiqa_shape(_ref_ret, dict(numpy=np.__version__, numba=numba.__version__, scipy=scipy.__version__,
+                                  threads=int(numba.get_num_threads())))
+    else:
+        main()

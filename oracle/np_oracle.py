@@ -224,12 +224,12 @@ def hybrid_rerank(cand_idx, cand_sparse, q8, q_scales, d8, d_scales, sparse_weig
     dense part is quantized_dot_product_batch (retriever_registry.py:90-117, pinned by tests/golden/int8.npz)
     restricted to the candidates.  Semantics checked against the CUDA path:
         dense  = f32((f64(int dot) * f64(qs)) * f64(ds))
-        score  = f32(f64(f32 ws) * f64(sparse) + f64(f32 wd) * f64(dense))      (dense alone if cand_sparse is None)
+        score  = f32(f64(ws) * f64(sparse) + f64(wd) * f64(dense))                (dense alone if cand_sparse is None)
     rank by score descending, document index ascending; candidates < 0 or outside the shard are skipped.
     Returns (idx i64[Q, k_out] padded with -1, score f32[Q, k_out] padded with -inf, dense f32[Q, k_in])."""
     cand_idx = np.asarray(cand_idx, np.int64)
     nq, k_in = cand_idx.shape
-    ws, wd = np.float64(np.float32(sparse_weight)), np.float64(np.float32(dense_weight))
+    ws, wd = np.float64(sparse_weight), np.float64(dense_weight)
     out_i = np.full((nq, k_out), -1, np.int64)
     out_v = np.full((nq, k_out), -np.inf, np.float32)
     dense_all = np.full((nq, k_in), -np.inf, np.float32)

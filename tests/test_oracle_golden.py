@@ -177,8 +177,74 @@ def test_hybrid_rerank_restatement_is_consistent_with_the_pinned_pieces():
             ok = (cand[q] >= base) & (cand[q] < base + n)
             assert np.array_equal(dense[q, ok], full[q, cand[q, ok] - base]) and np.isneginf(dense[q, ~ok]).all()
             fused = dense[q, ok] if sp is None else (
-                np.float64(np.float32(0.3)) * sp[q, ok].astype(np.float64)
-                + np.float64(np.float32(0.7)) * dense[q, ok].astype(np.float64)).astype(np.float32)
+                np.float64(0.3) * sp[q, ok].astype(np.float64)
+                + np.float64(0.7) * dense[q, ok].astype(np.float64)).astype(np.float32)
             order = np.lexsort((cand[q, ok], -fused))[:k_out]
             assert np.array_equal(idx[q, :len(order)], cand[q, ok][order])
             assert np.array_equal(val[q, :len(order)], fused[order])
+
+
+# ----------------------------------------------------------------------------------- BASELINE config 1
+def _load_synthetic_module():
+    """b200ret/synthetic.py is numpy-only: load it without the package (no CUDA library needed)."""
+    import importlib.util
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(
+        "b2r_synthetic", os.path.join(here, "optimized-sparse-retrieval-for-high-performance-rag-pipelines_b200",
+                                      "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_fiqa_shape_config1_oracle_vs_reference(golden_dir):
+    """BASELINE config 1 at its full size (57,638 docs, 648 queries, top-10): the restated corpus generator
+    reproduces the reference generator's corpus (sha256 recorded by oracle/gen_golden.py), and the oracle's
+    text-level restatement gives the canonical top-10 of the reference's own score vectors bit for bit."""
+    z = np.load(os.path.join(golden_dir, "fiqa_shape.npz"))
+    meta = json.loads(str(z["meta"]))
+    syn = _load_synthetic_module()
+    corpus = syn.fiqa_shape_corpus()
+    assert syn.corpus_sha256(corpus) == meta["corpus_sha256"]
+    queries = syn.fiqa_shape_queries()
+    ix = np_oracle.build_text_index(corpus)
+    assert len(ix["doc_ids"]) == meta["n_docs"] and len(ix["vocabulary"]) == meta["vocab_size"]
+    assert len(ix["data"]) == meta["nnz"] and ix["avgdl"] == meta["avgdl"]
+    assert float(np.sum(ix["idf"].astype(np.float64))) == meta["idf_sum"]
+    # pack the queries like RetrievalService._score_bm25_query does (retrieval.py:236-252)
+    from collections import Counter
+    ptr, terms, weights, live = [0], [], [], []
+    for qi, text in enumerate(queries.values()):
+        c = Counter(np_oracle.tokenize(text))
+        tw = sorted((ix["vocabulary"][t], float(n)) for t, n in c.items() if t in ix["vocabulary"])
+        if tw:
+            live.append(qi)
+            terms += [t for t, _ in tw]
+            weights += [w for _, w in tw]
+            ptr.append(len(terms))
+    k = z["canon_idx"].shape[1]
+    gi, gv = c_oracle.bm25_search_batch(np.asarray(ptr, np.int32), np.asarray(terms, np.int32),
+                                        np.asarray(weights, np.float32), len(ix["vocabulary"]), ix["data"],
+                                        ix["indices"], ix["indptr"], ix["doc_lengths"], ix["idf"], 1.2, 0.75,
+                                        ix["avgdl"], k)
+    assert np.array_equal(gi, z["canon_idx"][live])
+    assert np.array_equal(gv.view(np.uint32), z["canon_val"][live].view(np.uint32))
+    dead = np.setdiff1d(np.arange(len(queries)), live)
+    assert (z["canon_idx"][dead] == -1).all() and (z["ref_idx"][dead] == -1).all()
+    # what search_bm25 itself returned: same scores as the canonical list (positive part); same ids wherever the
+    # reference's unspecified tie order is not in play
+    n_empty = 0
+    for qi in range(len(queries)):
+        pos = z["canon_val"][qi] > 0
+        n_ref = int((z["ref_idx"][qi] >= 0).sum())
+        n_empty += n_ref == 0
+        assert n_ref == int(pos.sum()), qi
+        assert np.array_equal(z["ref_val"][qi, :n_ref], z["canon_val"][qi, :n_ref]), qi
+        untied = np.ones(n_ref, bool)
+        v = z["canon_val"][qi, :n_ref]
+        untied[1:] &= v[1:] != v[:-1]
+        untied[:-1] &= v[:-1] != v[1:]
+        if n_ref == k:
+            untied &= v != v[-1]            # the boundary value may tie with documents outside the list
+        assert np.array_equal(z["ref_idx"][qi, :n_ref][untied], z["canon_idx"][qi, :n_ref][untied]), qi
+    assert n_empty == meta["n_empty_results"]

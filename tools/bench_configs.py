@@ -19,6 +19,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import b200ret  # noqa: E402
 from b200ret import synthetic as S  # noqa: E402
 
@@ -42,46 +43,7 @@ def timed(fn, steps=5, warmup=2):
     return a.elapsed_time(b) / steps
 
 
-def zipf_csr_torch(n_docs, n_vocab, mean_len, seed, dev, distinct_per_doc=None, chunk=1 << 20):
-    """GPU version of synthetic.zipf_corpus (different RNG stream, same law)."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    p = 1.0 / torch.arange(1, n_vocab + 1, dtype=torch.float64, device=dev)
-    cdf = torch.cumsum(p / p.sum(), 0)
-    datas, inds, nnz_rows, lens_all = [], [], [], []
-    for lo in range(0, n_docs, chunk):
-        n = min(chunk, n_docs - lo)
-        if distinct_per_doc is None:
-            gam = torch.distributions.Gamma(torch.tensor(2.0, device=dev), torch.tensor(2.0 / mean_len, device=dev))
-            torch.manual_seed(seed + lo)
-            lens = torch.clamp(torch.floor(gam.sample((n,))), 5, 400).to(torch.int64)
-        else:
-            lens = torch.full((n,), distinct_per_doc * 3, dtype=torch.int64, device=dev)
-        tot = int(lens.sum())
-        toks = torch.clamp(torch.searchsorted(cdf, torch.rand(tot, device=dev, generator=g, dtype=torch.float64)),
-                           max=n_vocab - 1)
-        doc = torch.repeat_interleave(torch.arange(n, device=dev), lens)
-        key, _ = torch.sort(doc * n_vocab + toks)
-        del toks, doc
-        uniq, cnt = torch.unique_consecutive(key, return_counts=True)
-        del key
-        rows = uniq // n_vocab
-        if distinct_per_doc is not None:      # keep the first `distinct_per_doc` terms of every row
-            start = torch.searchsorted(rows, torch.arange(n, device=dev))
-            rank = torch.arange(len(uniq), device=dev) - start[rows]
-            keep = rank < distinct_per_doc
-            uniq, cnt, rows = uniq[keep], cnt[keep], rows[keep]
-        nnz_rows.append(torch.bincount(rows, minlength=n))
-        inds.append((uniq % n_vocab).to(torch.int32))
-        if distinct_per_doc is None:
-            datas.append(cnt.to(torch.float32))
-            lens_all.append(lens.to(torch.float32))
-        else:
-            gam = torch.distributions.Gamma(torch.tensor(2.0, device=dev), torch.tensor(2.0, device=dev))
-            datas.append(gam.sample((len(uniq),)).to(torch.float32))
-    indptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(torch.cat(nnz_rows), 0, out=indptr[1:])
-    return torch.cat(datas), torch.cat(inds), indptr, (torch.cat(lens_all) if lens_all else None)
+from gpu_synth import zipf_csr_torch  # noqa: E402
 
 
 def run_int8(args):
