@@ -16,6 +16,7 @@ libb200ret.so through the C ABI.  The doc-major scipy CSR the reference builds
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Iterable, Optional, Sequence, Tuple
 
 import numpy as np
@@ -112,8 +113,12 @@ class TermMajorIndex:
         self.idf_host: Optional[np.ndarray] = None
         self._desc = _abi.B2RIndex()
         self._bufs = {}
-        self._ws: Optional[torch.Tensor] = None
+        # Concurrency (the reference's search_bm25 may be called from several threads): the workspace is kept per
+        # CUDA stream, so searches enqueued on different streams never share scratch memory; search_host, which
+        # also owns pinned staging buffers, holds _lock from the fill to the copy-out.
+        self._ws_by_stream = {}
         self._pinned = {}
+        self._lock = threading.Lock()
         self.workspace_cap_bytes = 16 << 30
 
     # ------------------------------------------------------------------ build
@@ -297,10 +302,18 @@ class TermMajorIndex:
         _abi.check(_abi.lib.b2r_search_workspace(C.byref(self._desc), n_queries, k, C.byref(mn), C.byref(full)),
                    "search workspace")
         want = min(full.value, max(mn.value, self.workspace_cap_bytes)) + extra
-        if self._ws is None or self._ws.numel() < want:
-            self._ws = None
-            self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
-        return self._ws
+        key = _stream_ptr(self.device)
+        ws = self._ws_by_stream.get(key)
+        if ws is None or ws.numel() < want:
+            self._ws_by_stream.pop(key, None)
+            ws = None
+            ws = self._ws_by_stream[key] = torch.empty(want, dtype=torch.uint8, device=self.device)
+        return ws
+
+    @property
+    def _ws(self) -> Optional[torch.Tensor]:
+        """Workspace of the current stream (None before the first search on it)."""
+        return self._ws_by_stream.get(_stream_ptr(self.device))
 
     # ------------------------------------------------------------------ search (device buffers)
     def search(self, q_ptr, q_terms, q_weights, k: int, *, return_keys: bool = False):
@@ -359,21 +372,22 @@ class TermMajorIndex:
         k = int(k)
         if k < 1:
             raise ValueError("k must be >= 1")
-        hp = self._pinned_buf("q_ptr", nq + 1, torch.int32)
-        ht = self._pinned_buf("q_terms", nt, torch.int32)
-        hw = self._pinned_buf("q_weights", nt, torch.float32)
-        hi = self._pinned_buf("idx", nq * k, torch.int64)
-        hv = self._pinned_buf("val", nq * k, torch.float32)
-        hp[:nq + 1].numpy()[:] = q_ptr
-        ht[:nt].numpy()[:] = q_terms
-        hw[:nt].numpy()[:] = q_weights
-        extra = int(_abi.lib.b2r_search_host_extra_bytes(nq, nt, k))
-        ws = self._workspace(nq, k, extra)
-        _abi.check(_abi.lib.b2r_search_batch_host(C.byref(self._desc), hp.data_ptr(), ht.data_ptr(), hw.data_ptr(),
-                                                  self.idf.data_ptr(), nq, k, None, hi.data_ptr(), hv.data_ptr(),
-                                                  ws.data_ptr(), ws.numel(), _stream_ptr(self.device)),
-                   "search (host buffers)")
-        return (hi[:nq * k].numpy().reshape(nq, k).copy(), hv[:nq * k].numpy().reshape(nq, k).copy())
+        with self._lock:      # the pinned staging buffers are per index: one host-buffer search at a time
+            hp = self._pinned_buf("q_ptr", nq + 1, torch.int32)
+            ht = self._pinned_buf("q_terms", nt, torch.int32)
+            hw = self._pinned_buf("q_weights", nt, torch.float32)
+            hi = self._pinned_buf("idx", nq * k, torch.int64)
+            hv = self._pinned_buf("val", nq * k, torch.float32)
+            hp[:nq + 1].numpy()[:] = q_ptr
+            ht[:nt].numpy()[:] = q_terms
+            hw[:nt].numpy()[:] = q_weights
+            extra = int(_abi.lib.b2r_search_host_extra_bytes(nq, nt, k))
+            ws = self._workspace(nq, k, extra)
+            _abi.check(_abi.lib.b2r_search_batch_host(C.byref(self._desc), hp.data_ptr(), ht.data_ptr(), hw.data_ptr(),
+                                                      self.idf.data_ptr(), nq, k, None, hi.data_ptr(), hv.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), _stream_ptr(self.device)),
+                       "search (host buffers)")
+            return (hi[:nq * k].numpy().reshape(nq, k).copy(), hv[:nq * k].numpy().reshape(nq, k).copy())
 
     # ------------------------------------------------------------------ traffic model
     def postings_touched(self, q_ptr: np.ndarray, q_terms: np.ndarray, df: np.ndarray) -> int:

@@ -75,12 +75,33 @@ def _ident(a) -> tuple:
     return ("n", a.__array_interface__["data"][0], a.shape, a.dtype.str)
 
 
+def _fingerprint(a) -> int:
+    """Cheap content fingerprint (64 strided samples + the last element) so that an in-place edit of a cached CSR
+    array is noticed in the common cases; identity of the arrays stays the primary key."""
+    n = int(a.shape[0]) if len(a.shape) else 0
+    if n == 0:
+        return 0
+    step = max(1, n // 64)
+    if isinstance(a, torch.Tensor):
+        smp = torch.cat([a[::step][:64].reshape(-1), a[-1:].reshape(-1)]).detach().cpu().numpy()
+    else:
+        smp = np.concatenate([np.asarray(a)[::step][:64].reshape(-1), np.asarray(a)[-1:].reshape(-1)])
+    return hash(smp.tobytes())
+
+
 def _cached_index(kind, data, indices, indptr, doc_lengths, n_vocab, k1, b, avgdl) -> TermMajorIndex:
+    """Index over the caller's CSR, cached on array identity + a sampled content fingerprint.  The reference
+    silently skips CSR term ids >= len(query_tf) (`if term_idx < len(query_tf)`, retrieval.py:66): the index is
+    therefore built over max(len(query_tf), max term id + 1) terms, and the extra terms can never be queried."""
     key = (kind, _ident(data), _ident(indices), _ident(indptr),
-           _ident(doc_lengths) if doc_lengths is not None else None, int(n_vocab), float(k1), float(b), float(avgdl))
+           _ident(doc_lengths) if doc_lengths is not None else None, int(n_vocab), float(k1), float(b), float(avgdl),
+           _fingerprint(data), _fingerprint(indices), _fingerprint(indptr))
     hit = _INDEX_CACHE.get(key)
     ix = hit[0] if hit is not None else None
     if ix is None:
+        if int(indptr[-1]) > 0:
+            top = int(indices.max()) + 1
+            n_vocab = max(int(n_vocab), top)
         ones = np.ones(n_vocab, np.float32)   # idf is a per-call input: set below
         ix = TermMajorIndex.from_csr(data, indices, indptr, doc_lengths, n_vocab=n_vocab, idf=ones,
                                      avgdl=avgdl, k1=k1, b=b, kind=kind)
@@ -90,6 +111,12 @@ def _cached_index(kind, data, indices, indptr, doc_lengths, n_vocab, k1, b, avgd
     else:
         _INDEX_CACHE.move_to_end(key)
     return ix
+
+
+def _fit(idf, n: int) -> np.ndarray:
+    """idf cut / zero-padded to the index's vocabulary (terms beyond len(query_tf) are never queried)."""
+    idf = np.asarray(idf, np.float32)
+    return idf[:n] if len(idf) >= n else np.concatenate([idf, np.zeros(n - len(idf), np.float32)])
 
 
 def _n_vocab_for(query_tf, idf_weights) -> int:
@@ -105,8 +132,7 @@ def simd_bm25_score(query_tf, doc_tf_data, doc_tf_indices, doc_tf_indptr, doc_le
     n_vocab = _n_vocab_for(q, idf_weights)
     ix = _cached_index("bm25", doc_tf_data, doc_tf_indices, doc_tf_indptr, doc_lengths, n_vocab, k1, b, avgdl)
     idf = idf_weights.detach().cpu().numpy() if isinstance(idf_weights, torch.Tensor) else np.asarray(idf_weights)
-    ix.set_idf(np.asarray(idf, np.float32)[:n_vocab] if len(idf) >= n_vocab else
-               np.concatenate([idf, np.zeros(n_vocab - len(idf), np.float32)]))
+    ix.set_idf(_fit(idf, ix.n_vocab))
     ptr, terms, w = queries_from_dense(q)
     s = ix.score_dense(ptr, terms, w)
     if q.ndim == 1:
@@ -124,7 +150,7 @@ def simd_tfidf_score(query_tf, doc_tf_data, doc_tf_indices, doc_tf_indptr, idf_w
     n_vocab = _n_vocab_for(q, idf_weights)
     ix = _cached_index("impact", doc_tf_data, doc_tf_indices, doc_tf_indptr, None, n_vocab, 0.0, 0.0, 0.0)
     idf = idf_weights.detach().cpu().numpy() if isinstance(idf_weights, torch.Tensor) else np.asarray(idf_weights)
-    ix.set_idf(np.asarray(idf, np.float32)[:n_vocab])
+    ix.set_idf(_fit(idf, ix.n_vocab))
     ptr, terms, w = queries_from_dense(q)
     s = ix.score_dense(ptr, terms, w)
     if q.ndim == 1:

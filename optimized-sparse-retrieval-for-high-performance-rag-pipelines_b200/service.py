@@ -154,14 +154,19 @@ class RetrievalService:
         if self.corpus_tf is None:
             raise ValueError("BM25 index not built. Call build_bm25_index() first.")
         path = Path(path)
+        if str(path).endswith(".npz"):
+            raise ValueError("save_bm25_index: the path names the binary HBM layout and must not end in .npz "
+                             "(the host attributes go to '<path>.meta.npz'; a .npz path is read back as a "
+                             "reference-style CSR cache)")
         self._sync_gpu_index().save(path)
         tf = self.corpus_tf
         with open(str(path) + ".meta.npz", "wb") as f:
             np.savez_compressed(
                 f, tf_data=tf.data, tf_indices=tf.indices, tf_indptr=tf.indptr, tf_shape=np.asarray(tf.shape),
                 doc_lengths=self.doc_lengths, idf=self.idf_weights,
-                vocabulary=np.asarray(sorted(self.vocabulary, key=self.vocabulary.get), dtype=object),
-                doc_ids=np.asarray(self.doc_ids, dtype=object), avgdl=self.avgdl, k1=self.k1, b=self.b)
+                vocabulary=np.asarray(sorted(self.vocabulary, key=self.vocabulary.get), dtype=np.str_),
+                doc_ids=np.asarray([str(d) for d in self.doc_ids], dtype=np.str_), avgdl=self.avgdl, k1=self.k1,
+                b=self.b)          # unicode arrays: nothing in the file needs pickle
 
     def load_bm25_index(self, path: Union[str, Path], verify: bool = True) -> None:
         """Inverse of save_bm25_index.  The HBM layout is read back as is (no build kernels) when `<path>` exists
@@ -169,7 +174,13 @@ class RetrievalService:
         .npz) it is rebuilt from the CSR."""
         path = Path(path)
         meta_path = Path(str(path) + ".meta.npz") if not str(path).endswith(".npz") else path
-        cached = np.load(meta_path, allow_pickle=True)
+        cached = np.load(meta_path, allow_pickle=False)
+        try:
+            cached["vocabulary"], cached["doc_ids"]
+        except ValueError:
+            # a cache written by the REFERENCE stores these two as object arrays (evaluate_rag_pipeline.py:280-293):
+            # only such a file is opened with pickle enabled -- load reference caches from trusted paths only
+            cached = np.load(meta_path, allow_pickle=True)
         shape = tuple(int(x) for x in cached["tf_shape"])
         self.corpus_tf = csr_matrix((cached["tf_data"], cached["tf_indices"], cached["tf_indptr"]), shape=shape)
         self.doc_lengths = np.asarray(cached["doc_lengths"], dtype=np.float32)
