@@ -156,7 +156,10 @@ __device__ __forceinline__ void apply_dense_term(uint32_t beg, uint32_t end, int
 enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1, SC_OUT_MAXIMA = 2 };
 enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1 };
 constexpr int SC_GROUPS_PER_TILE = 32 * B2R_SUBTILES;  // MAXIMA: one group maximum per lane
-constexpr int SC_MAX_SLOTS = 4;                        // queries a CTA works on side by side
+#ifndef SC_MAX_SLOTS_DEF
+#define SC_MAX_SLOTS_DEF 4
+#endif
+constexpr int SC_MAX_SLOTS = SC_MAX_SLOTS_DEF;         // queries a CTA works on side by side
 constexpr int SC_REC_CAP = 2048;                       // term records of a CTA's query range staged in shared memory
 constexpr int SC_SLAB_SUB = B2R_SLAB_TILE_DOCS / B2R_SUBTILES;   // 256 documents per slab
 constexpr int SC_SLAB_PAIRS = SC_SLAB_SUB / 64;        // double2 accumulators per lane in the register layout
@@ -185,7 +188,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
                    const void *__restrict__ slab_val, int n_slabs, int n_tiles, int tile_docs,
                    const int32_t *__restrict__ q_ptr, const int32_t *__restrict__ q_terms,
                    const float *__restrict__ q_weights, const float *__restrict__ idf, int q0, int nq, int range_len,
-                   int tile_mode, int tile_step, ScoreOut o) {
+                   int tile_mode, int tile_step, int diag, ScoreOut o) {
     using val_t = typename std::conditional<KIND == B2R_KIND_BM25, double, float>::type;
     using val2_t = typename std::conditional<KIND == B2R_KIND_BM25, double2, float2>::type;
     extern __shared__ __align__(128) unsigned char sc_smem[];
@@ -363,6 +366,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
                 if (beg == end) continue;  // warp-uniform
                 const typename TermW<KIND>::type w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
                 const int kind = __shfl_sync(full, my_kind, j);
+                if (diag && kind == 0) continue;   // B2R_SCORE_DIAG=1: measurement only (sparse terms skipped: wrong results)
                 if (SLABS && kind >= 2) {
                     if (!in_reg) {
                         if (first) {
@@ -477,6 +481,329 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     }  // query loop
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The scorer for tile_docs == B2R_SLAB_TILE_DOCS (the default layout): same tile-stationary scheme as above, written
+// for instruction count -- the round-1 kernel and the generic kernel above spend most of their issue slots on per-
+// (query, sub-tile) overhead (term staging, shuffles, threshold set-up), not on postings.  Here everything that does
+// not depend on the warp is computed ONCE per CTA and chunk of queries and kept in shared memory:
+//   rec[i]  one 16-byte record per query term {idf, query weight, first posting, kind word}, in term order
+//           kind word: [7:0] 0 sparse / 1 dense / 2 + h head row h; [15:8] sub-tile mask (sparse: sub-tiles of this
+//           tile that hold a posting of the term; head: sub-tiles whose segment has a slab); [31:16] sparse: postings
+//           of the term in this tile
+//   cum[i]  dense and head terms: the 9 sub-tile offsets of the term's postings in this tile, relative, u16
+//   qthr[q] FUSED: the query's candidate threshold as a key and as the f64 bound the accumulators are compared with
+// A (query, sub-tile) task is then a loop over records read by broadcast loads: no shuffles, no global loads before
+// the postings themselves, all loop bounds constant.  A sparse term whose block has no posting in the warp's
+// sub-tile costs one record load and a bit test.
+constexpr int T2K_TILE = B2R_SLAB_TILE_DOCS;
+constexpr int T2K_SUB = T2K_TILE / B2R_SUBTILES;        // 256 documents per warp
+constexpr int T2K_PAIRS = T2K_SUB / 64;                 // double2 accumulators per lane
+constexpr int T2K_SLOTS = 4;
+constexpr int T2K_REC_CAP = 704;                        // term records per chunk of queries
+constexpr int T2K_Q_CAP = 128;                          // queries per chunk
+constexpr int T2K_CUM = 10;                             // u16 per record in cum[] (9 used)
+static_assert(T2K_PAIRS == SC_SLAB_PAIRS && T2K_SUB == SC_SLAB_SUB, "slab layout");
+
+struct __align__(16) T2KRec {
+    float idf, w;
+    uint32_t base, kind;
+};
+struct __align__(16) T2KThr {
+    uint64_t thr;
+    double lo;
+};
+
+template <int KIND>
+constexpr size_t t2k_smem_bytes() {
+    return (size_t)T2K_SLOTS * T2K_TILE * 8 + (size_t)B2R_HEAD_TERMS * T2K_TILE * (KIND == B2R_KIND_BM25 ? 8 : 4) +
+           (size_t)T2K_REC_CAP * sizeof(T2KRec) + (size_t)T2K_REC_CAP * T2K_CUM * 2 + (size_t)(T2K_Q_CAP + 4) * 4 +
+           (size_t)T2K_Q_CAP * sizeof(T2KThr);
+}
+
+// record of query term j for doc tile `tile` (see above); okm[h] = sub-tiles of this tile in which head row h has a slab
+__device__ __forceinline__ T2KRec t2k_make_record(int j, int tile, int n_tiles, const int32_t *__restrict__ q_terms,
+                                                  const float *__restrict__ q_weights, const float *__restrict__ idf,
+                                                  const int32_t *__restrict__ dense_id, const uint32_t *__restrict__ dense_ptr,
+                                                  const uint32_t *__restrict__ blk_ptr, const uint32_t *__restrict__ post_doc,
+                                                  const int *okm, bool slabs, uint16_t *cum_out) {
+    T2KRec rc;
+    const int t = q_terms[j];
+    rc.w = q_weights[j];
+    rc.idf = idf[t];
+    const int32_t did = dense_id[t];
+    if (did >= 0) {
+        const uint32_t *row = dense_ptr + (size_t)did * ((size_t)n_tiles * B2R_SUBTILES + 1) + (size_t)tile * B2R_SUBTILES;
+        const uint32_t o0 = row[0];
+        cum_out[0] = 0;
+#pragma unroll
+        for (int sg = 1; sg <= B2R_SUBTILES; ++sg) cum_out[sg] = (uint16_t)(row[sg] - o0);
+        rc.base = o0;
+        rc.kind = 1;
+        // slabs add (idf * 0) * q for absent documents: only exact when both weights are finite
+        if (slabs && did < B2R_HEAD_TERMS && isfinite(rc.idf) && isfinite(rc.w)) rc.kind = (2u + did) | ((uint32_t)okm[did] << 8);
+    } else {
+        const size_t e = (size_t)t * n_tiles + tile;
+        const uint32_t beg = blk_ptr[e], n = blk_ptr[e + 1] - beg;
+        uint32_t mask = n > 16 ? 0xFFu : 0u;
+        if (n <= 16)
+            for (uint32_t p = 0; p < n; ++p) mask |= 1u << (((post_doc[beg + p] - (uint32_t)tile * T2K_TILE) / T2K_SUB) & 7);
+        rc.base = beg;
+        rc.kind = (mask << 8) | (n << 16);
+    }
+    return rc;
+}
+
+template <int KIND, int OUT>
+__global__ void __launch_bounds__(T2K_SLOTS * SC_THREADS, 1)
+score_t2k_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
+                 const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
+                 const uint32_t *__restrict__ dense_ptr, const int32_t *__restrict__ slab_idx,
+                 const void *__restrict__ slab_val, int n_slabs, int n_tiles, const int32_t *__restrict__ q_ptr,
+                 const int32_t *__restrict__ q_terms, const float *__restrict__ q_weights, const float *__restrict__ idf,
+                 int q0, int nq, int range_len, int tile_mode, int tile_step, ScoreOut o) {
+    using val_t = typename std::conditional<KIND == B2R_KIND_BM25, double, float>::type;
+    using val2_t = typename std::conditional<KIND == B2R_KIND_BM25, double2, float2>::type;
+    extern __shared__ __align__(128) unsigned char sc_smem[];
+    __shared__ __align__(8) uint64_t cbar;   // "the slabs of this tile have landed"
+    __shared__ int okm[B2R_HEAD_TERMS];      // per head row: sub-tiles of this tile whose segment has a slab
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = warp / B2R_SUBTILES, w = warp % B2R_SUBTILES;
+    const int y = blockIdx.y;
+    const int tile = tile_mode == SC_TILES_ALL ? y : y * tile_step;
+    const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
+    const int r0 = blockIdx.x * range_len, r1 = min(nq, r0 + range_len);
+    const bool slabs = slab_idx != nullptr && n_slabs > 0;
+
+    double *acc_w = reinterpret_cast<double *>(sc_smem) + (size_t)slot * T2K_TILE + (size_t)w * T2K_SUB;
+    unsigned char *sp = sc_smem + (size_t)T2K_SLOTS * T2K_TILE * 8;
+    const val_t *cache = reinterpret_cast<const val_t *>(sp);
+    sp += (size_t)B2R_HEAD_TERMS * T2K_TILE * sizeof(val_t);
+    T2KRec *rec = reinterpret_cast<T2KRec *>(sp);
+    sp += (size_t)T2K_REC_CAP * sizeof(T2KRec);
+    uint16_t *cum = reinterpret_cast<uint16_t *>(sp);
+    sp += (size_t)T2K_REC_CAP * T2K_CUM * 2;
+    int *qoff = reinterpret_cast<int *>(sp);
+    sp += (size_t)(T2K_Q_CAP + 4) * 4;
+    T2KThr *qthr = reinterpret_cast<T2KThr *>(sp);
+
+    if (OUT == SC_OUT_DENSE && o.gate != nullptr) {   // a gated launch is expected to find nothing to do
+        int any = 0;
+        for (int ql = r0 + (int)threadIdx.x; ql < r1; ql += blockDim.x) any |= o.gate[ql] > o.gate_cap;
+        if (!__syncthreads_or(any)) return;
+    }
+    // ---- the tile's slabs -> shared memory (one bulk copy per (head row, sub-tile) that has one)
+    const uint32_t cbar_a = sc_smem_u32(&cbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cbar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < B2R_HEAD_TERMS) okm[threadIdx.x] = 0;
+    __syncthreads();
+    if (warp == 0 && slabs) {
+        uint32_t bytes = 0;
+        for (int i = lane; i < B2R_HEAD_TERMS * B2R_SUBTILES; i += 32) {
+            const int h = i / B2R_SUBTILES, sseg = i % B2R_SUBTILES;
+            const int32_t sid = slab_idx[(size_t)h * n_seg + (size_t)tile * B2R_SUBTILES + sseg];
+            if (sid >= 0 && sid < n_slabs) {
+                atomicOr(&okm[h], 1 << sseg);
+                const uint32_t nb = (uint32_t)(T2K_SUB * sizeof(val_t));
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        sc_smem_u32(cache + (size_t)h * T2K_TILE + (size_t)sseg * T2K_SUB)),
+                    "l"(static_cast<const val_t *>(slab_val) + (size_t)sid * T2K_SUB), "r"(nb), "r"(cbar_a)
+                    : "memory");
+                bytes += nb;
+            }
+        }
+#pragma unroll
+        for (int ofs = 16; ofs; ofs >>= 1) bytes += __shfl_xor_sync(full, bytes, ofs);
+        // (a copy that completes before this arrive only drives the transaction count negative for a moment:
+        // the phase cannot complete before the one pending arrival below)
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cbar_a), "r"(bytes) : "memory");
+    } else if (threadIdx.x == 0 && !slabs) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cbar_a) : "memory");
+    }
+    __syncthreads();   // okm is complete
+
+    const uint32_t my_doc0 = (uint32_t)tile * T2K_TILE + (uint32_t)w * T2K_SUB;
+    bool cache_ready = false;
+    for (int cur = r0; cur < r1;) {
+        // ---- chunk of queries [cur, cur + c): as many as fit the record and query capacities (at least one)
+        const int cnt = min(r1 - cur, T2K_Q_CAP);
+        const int tb = q_ptr[q0 + cur];
+        int fits = 0;
+        if ((int)threadIdx.x < cnt) fits = q_ptr[q0 + cur + threadIdx.x + 1] - tb <= T2K_REC_CAP;
+        int c = __syncthreads_count(fits);   // (q_ptr is monotone: the queries that fit form a prefix)
+        if (c < 1) c = 1;
+        const int n_staged = min(q_ptr[q0 + cur + c] - tb, T2K_REC_CAP);
+        for (int i = threadIdx.x; i < n_staged; i += blockDim.x)
+            rec[i] = t2k_make_record(tb + i, tile, n_tiles, q_terms, q_weights, idf, dense_id, dense_ptr, blk_ptr, post_doc,
+                                     okm, slabs, cum + (size_t)i * T2K_CUM);
+        for (int i = threadIdx.x; i <= c; i += blockDim.x) qoff[i] = q_ptr[q0 + cur + i] - tb;
+        if (OUT == SC_OUT_FUSED) {
+            for (int i = threadIdx.x; i < c; i += blockDim.x) {
+                const uint64_t thr = o.thr_keys[cur + i];
+                const uint32_t thr_hi = (uint32_t)(thr >> 32);
+                // A document can only beat thr if f32(acc) >= the threshold score.  The accumulators are compared in
+                // f64 against the f32 value just below the threshold score: acc < pred(thr_f) implies f32(acc) <=
+                // pred(thr_f) < thr_f (rounding is monotone); only survivors are converted and keyed.  Ordered
+                // encoding: -1 = next smaller f32; 0x7fffffff would be -0.0 (== +0.0 in the ranking): skip it; at or
+                // below -inf (0x007fffff) there is nothing smaller: no filter (thr_hi == 0: no threshold at all)
+                uint32_t thr_ord = thr_hi > 0x007fffffu ? thr_hi - 1u : 0u;
+                if (thr_ord == 0x7fffffffu) thr_ord = 0x7ffffffeu;
+                double lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
+                // "strictly positive scores only" (kth_of_maxima's positive floor): nothing below 2^-150 rounds to a
+                // positive f32, so the untouched documents (acc == 0) never reach the conversion path
+                if (thr == ((0x80000000ull << 32) | 0xFFFFFFFFull)) lo = __longlong_as_double(0x3690000000000000ll);
+                qthr[i].thr = thr;
+                qthr[i].lo = lo;
+            }
+        }
+        __syncthreads();
+        if (!cache_ready) {
+            sc_mbar_wait(cbar_a, 0);   // the slab bytes are visible
+            cache_ready = true;
+        }
+
+        for (int qi = slot; qi < c; qi += T2K_SLOTS) {
+            const int ql = cur + qi;
+            if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap) continue;
+            const int i0 = qoff[qi], i1 = qoff[qi + 1];
+            // where the sub-tile's accumulators are (warp-uniform): 0 nowhere yet (all +0.0), 1 registers, 2 shared memory
+            int st = 0;
+            double2 r[T2K_PAIRS];
+#pragma unroll
+            for (int cc = 0; cc < T2K_PAIRS; ++cc) r[cc] = make_double2(0.0, 0.0);
+            auto to_smem = [&]() {
+                if (st == 2) return;
+#pragma unroll
+                for (int cc = 0; cc < T2K_PAIRS; ++cc) *reinterpret_cast<double2 *>(acc_w + 64 * cc + 2 * lane) = r[cc];
+                st = 2;     // (r[] holds zeros in state 0)
+                __syncwarp();
+            };
+            for (int i = i0; i < i1; ++i) {
+                T2KRec rc;
+                uint16_t cum_l[T2K_CUM];
+                const bool staged = i < n_staged;
+                if (staged) rc = rec[i];
+                else rc = t2k_make_record(tb + i, tile, n_tiles, q_terms, q_weights, idf, dense_id, dense_ptr, blk_ptr, post_doc,
+                                          okm, slabs, cum_l);     // (a query longer than the record capacity)
+                const uint32_t kind = rc.kind & 0xFFu;
+                if (kind >= 2u && ((rc.kind >> (8 + w)) & 1u)) {
+                    // ---- slab: register accumulators
+                    if (st == 2) {
+#pragma unroll
+                        for (int cc = 0; cc < T2K_PAIRS; ++cc)
+                            r[cc] = *reinterpret_cast<const double2 *>(acc_w + 64 * cc + 2 * lane);
+                    }
+                    st = 1;
+                    const val2_t *cv = reinterpret_cast<const val2_t *>(cache + (size_t)(kind - 2u) * T2K_TILE +
+                                                                        (size_t)w * T2K_SUB) + lane;
+                    if (KIND == B2R_KIND_BM25) {
+                        const double wi = (double)rc.idf, wq = (double)rc.w;
+#pragma unroll
+                        for (int cc = 0; cc < T2K_PAIRS; ++cc) {
+                            const val2_t u = cv[32 * cc];
+                            r[cc].x = __dadd_rn(r[cc].x, __dmul_rn(__dmul_rn(wi, (double)u.x), wq));
+                            r[cc].y = __dadd_rn(r[cc].y, __dmul_rn(__dmul_rn(wi, (double)u.y), wq));
+                        }
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < T2K_PAIRS; ++cc) {
+                            const val2_t u = cv[32 * cc];
+                            // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens
+                            r[cc].x = __dadd_rn(r[cc].x, (double)__fmul_rn(__fmul_rn((float)u.x, rc.w), rc.idf));
+                            r[cc].y = __dadd_rn(r[cc].y, (double)__fmul_rn(__fmul_rn((float)u.y, rc.w), rc.idf));
+                        }
+                    }
+                } else if (kind >= 1u) {
+                    // ---- dense term (or a head term whose segment has no slab here): my bank-scheduled segment
+                    uint32_t cb, ce;
+                    if (staged) {
+                        cb = cum[(size_t)i * T2K_CUM + w];
+                        ce = cum[(size_t)i * T2K_CUM + w + 1];
+                    } else {
+                        cb = cum_l[w];
+                        ce = cum_l[w + 1];
+                    }
+                    if (cb == ce) continue;
+                    to_smem();
+                    apply_dense_term<KIND, false>(rc.base + cb, rc.base + ce, lane, my_doc0, post_doc, post_val, acc_w, rc.idf, rc.w);
+                    __syncwarp();
+                } else {
+                    // ---- sparse term: the tile's block, shared by all warps (kept in L1); the mask says whether it has
+                    // a posting in my sub-tile (blocks of more than 16 postings are always scanned)
+                    if (!((rc.kind >> (8 + w)) & 1u)) continue;
+                    const uint32_t n = rc.kind >> 16;
+                    to_smem();
+                    const double w_idf64 = (double)rc.idf, w_q64 = (double)rc.w;
+                    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+                        const uint32_t p = p0 + lane;
+                        if (p < n) {
+                            const uint32_t rel = __ldg(post_doc + rc.base + p) - my_doc0;
+                            if (rel < (uint32_t)T2K_SUB) {
+                                const double u = load_val<KIND>(post_val, rc.base + p);
+                                apply_posting<KIND, false>(acc_w, rel, u, rc.idf, rc.w, w_idf64, w_q64);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+
+            // ---- epilogue over the sub-tile's accumulators: pair (i, i + 1), i = 64 cc + 2 lane
+            if (st == 2) {
+#pragma unroll
+                for (int cc = 0; cc < T2K_PAIRS; ++cc) r[cc] = *reinterpret_cast<const double2 *>(acc_w + 64 * cc + 2 * lane);
+            }
+            if (OUT == SC_OUT_DENSE) {
+                float *out_row = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * T2K_TILE + w * T2K_SUB + 2 * lane;
+#pragma unroll
+                for (int cc = 0; cc < T2K_PAIRS; ++cc)
+                    *reinterpret_cast<float2 *>(out_row + 64 * cc) =
+                        make_float2(__double2float_rn(r[cc].x), __double2float_rn(r[cc].y));
+            } else if (OUT == SC_OUT_MAXIMA) {
+                // one maximum per lane over the (valid) documents it owns; f32(max) == max(f32): rounding is monotone
+                double m = -__longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll
+                for (int cc = 0; cc < T2K_PAIRS; ++cc) {
+                    const uint32_t doc = my_doc0 + 64 * cc + 2 * lane;
+                    if (doc < o.n_docs) m = fmax(m, r[cc].x);
+                    if (doc + 1 < o.n_docs) m = fmax(m, r[cc].y);
+                }
+                o.scores[(int64_t)ql * o.scores_stride + (int64_t)y * SC_GROUPS_PER_TILE + w * 32 + lane] = __double2float_rn(m);
+            } else {
+                const T2KThr th = qthr[qi];
+                bool any = false;
+#pragma unroll
+                for (int cc = 0; cc < T2K_PAIRS; ++cc) any |= (r[cc].x >= th.lo) | (r[cc].y >= th.lo);
+                if (any) {
+#pragma unroll
+                    for (int cc = 0; cc < T2K_PAIRS; ++cc) {
+                        const double av[2] = {r[cc].x, r[cc].y};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const uint32_t doc = my_doc0 + 64 * cc + 2 * lane + e;
+                            if (av[e] >= th.lo && doc < o.n_docs) {
+                                const uint64_t key = make_key(ord_f32(__double2float_rn(av[e])), o.doc_id_base + doc);
+                                if (key > th.thr) {
+                                    const int slot_c = atomicAdd(o.cand_cnt + ql, 1);
+                                    if (slot_c < o.cap) o.cand[(int64_t)ql * o.cap + slot_c] = key;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();   // the next query's writes must not overtake this epilogue's reads
+        }  // queries of the chunk
+        __syncthreads();   // the records are about to be replaced
+        cur += c;
+    }
+}
+
 constexpr size_t SC_SMEM_MAX = 226 * 1024;   // dynamic shared memory of a scorer CTA (227 KB minus the static part)
 
 struct ScoreLaunch {
@@ -488,10 +815,6 @@ struct ScoreLaunch {
 
 static bool g_slabs_enabled = true;   // b2r_set_slabs: test / profiling hook (same results either way)
 
-static bool use_slabs(const b2r_index *ix) {
-    return g_slabs_enabled && ix->slab_idx && ix->slab_val && ix->n_slabs > 0 && ix->tile_docs == B2R_SLAB_TILE_DOCS;
-}
-
 // CTAs per doc tile (= query ranges): enough CTAs for several waves over the 148 SMs, but every CTA should walk
 // enough queries to pay for its slab copy (B2R_SCORE_RANGES overrides: tuning experiments only)
 static int ranges_override() {
@@ -500,6 +823,14 @@ static int ranges_override() {
     return v >= 1 && v <= 65535 ? v : 0;
 }
 static const int g_ranges_override = ranges_override();
+static const int g_generic_scorer = [] {   // B2R_GENERIC_SCORER=1: tile 2048 through the generic kernel (A/B only)
+    const char *e = getenv("B2R_GENERIC_SCORER");
+    return e ? atoi(e) : 0;
+}();
+static const int g_score_diag = [] {
+    const char *e = getenv("B2R_SCORE_DIAG");
+    return e ? atoi(e) : 0;
+}();
 
 template <int KIND, int OUT, bool SLABS>
 static int launch_score_impl(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
@@ -527,7 +858,36 @@ static int launch_score_impl(const ScoreLaunch &L, int q0, int nq, int tile_mode
     kern<<<grid, slots * SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
                                                    ix->slab_idx, ix->slab_val, ix->n_slabs, ix->n_tiles, ix->tile_docs,
                                                    L.q_ptr, L.q_terms, L.q_weights, L.idf, q0, nq, range_len, tile_mode,
-                                                   tile_step, o);
+                                                   tile_step, OUT == SC_OUT_FUSED ? g_score_diag : 0, o);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
+
+template <int KIND, int OUT>
+static int launch_score_t2k(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
+    const b2r_index *ix = L.ix;
+    // CTAs per doc tile (= query ranges): several waves over the 148 SMs, but at least ~32 queries per CTA so that the
+    // slab copy and the record staging are paid for
+    int ranges = g_ranges_override ? g_ranges_override : (148 * 8 + n_y - 1) / n_y;
+    const int max_ranges = (nq + 31) / 32;
+    if (ranges > max_ranges) ranges = max_ranges;
+    if (ranges < 1) ranges = 1;
+    const int range_len = (nq + ranges - 1) / ranges;
+    ranges = (nq + range_len - 1) / range_len;
+    auto kern = score_t2k_kernel<KIND, OUT>;
+    constexpr size_t smem = t2k_smem_bytes<KIND>();
+    static_assert(smem <= SC_SMEM_MAX, "t2k shared memory");
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const bool slabs = g_slabs_enabled && ix->slab_idx && ix->slab_val && ix->n_slabs > 0;
+    dim3 grid((unsigned)ranges, (unsigned)n_y);
+    kern<<<grid, T2K_SLOTS * SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
+                                                       slabs ? ix->slab_idx : nullptr, ix->slab_val, slabs ? ix->n_slabs : 0,
+                                                       ix->n_tiles, L.q_ptr, L.q_terms, L.q_weights, L.idf, q0, nq, range_len,
+                                                       tile_mode, tile_step, o);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
@@ -536,13 +896,12 @@ template <int OUT>
 static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
     if (nq == 0 || n_y == 0) return B2R_OK;
     const b2r_index *ix = L.ix;
-    // a gated launch is expected to do nothing: it never copies slabs
-    const bool slabs = use_slabs(ix) && !(OUT == SC_OUT_DENSE && o.gate != nullptr);
-    if (ix->kind == B2R_KIND_BM25)
-        return slabs ? launch_score_impl<B2R_KIND_BM25, OUT, true>(L, q0, nq, tile_mode, tile_step, n_y, o)
-                     : launch_score_impl<B2R_KIND_BM25, OUT, false>(L, q0, nq, tile_mode, tile_step, n_y, o);
-    return slabs ? launch_score_impl<B2R_KIND_IMPACT, OUT, true>(L, q0, nq, tile_mode, tile_step, n_y, o)
-                 : launch_score_impl<B2R_KIND_IMPACT, OUT, false>(L, q0, nq, tile_mode, tile_step, n_y, o);
+    if (ix->tile_docs == T2K_TILE && !g_generic_scorer) {
+        if (ix->kind == B2R_KIND_BM25) return launch_score_t2k<B2R_KIND_BM25, OUT>(L, q0, nq, tile_mode, tile_step, n_y, o);
+        return launch_score_t2k<B2R_KIND_IMPACT, OUT>(L, q0, nq, tile_mode, tile_step, n_y, o);
+    }
+    if (ix->kind == B2R_KIND_BM25) return launch_score_impl<B2R_KIND_BM25, OUT, false>(L, q0, nq, tile_mode, tile_step, n_y, o);
+    return launch_score_impl<B2R_KIND_IMPACT, OUT, false>(L, q0, nq, tile_mode, tile_step, n_y, o);
 }
 
 static int check_index(const b2r_index *ix) {
