@@ -440,60 +440,62 @@ dense_head_kernel(const uint32_t *__restrict__ blk_ptr, int32_t n_vocab, int n_t
 }
 
 // ---- pass 7: slabs ----------------------------------------------------------------------------------
-// A (head term, sub-tile) segment with postings for a large share of the sub-tile's documents is ALSO stored as a
+// A (dense term, sub-tile) segment with postings for a large share of the sub-tile's documents is ALSO stored as a
 // slab: the sub-tile's values in document order, 0 where a document has no posting (include/b200ret.h, b2r_index).
 // Marking (here, inside b2r_index_build) only numbers the slabs; the values are filled by b2r_index_build_slabs once
-// the caller has allocated exactly n_slabs of them.  grid = B2R_HEAD_TERMS CTAs, one per head row.
+// the caller has allocated exactly n_slabs of them.  grid = (dense rows, segment chunks).
 __global__ void __launch_bounds__(BLD_THREADS)
 slab_mark_kernel(const uint32_t *__restrict__ dense_ptr, int n_tiles, int32_t n_dense_max, const int32_t *__restrict__ n_dense,
                  uint32_t slab_min, int32_t *__restrict__ slab_idx, int32_t *__restrict__ counter) {
-    const int h = blockIdx.x;
-    if (h >= min(*n_dense, n_dense_max)) return;
+    const int nd = min(*n_dense, n_dense_max);
     const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
-    const uint32_t *row = dense_ptr + (size_t)h * (n_seg + 1);
-    int32_t *out = slab_idx + (size_t)h * n_seg;
-    for (size_t seg = threadIdx.x; seg < n_seg; seg += blockDim.x) {
-        const uint32_t n = row[seg + 1] - row[seg];
-        out[seg] = n >= slab_min ? atomicAdd(counter, 1) : -1;
+    for (int h = blockIdx.x; h < nd; h += gridDim.x) {
+        const uint32_t *row = dense_ptr + (size_t)h * (n_seg + 1);
+        int32_t *out = slab_idx + (size_t)h * n_seg;
+        for (size_t seg = (size_t)blockIdx.y * blockDim.x + threadIdx.x; seg < n_seg; seg += (size_t)gridDim.y * blockDim.x) {
+            const uint32_t n = row[seg + 1] - row[seg];
+            out[seg] = n >= slab_min ? atomicAdd(counter, 1) : -1;
+        }
     }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(BLD_THREADS)
 slab_fill_kernel(const uint32_t *__restrict__ dense_ptr, const int32_t *__restrict__ slab_idx, int n_tiles, int tile_docs,
-                 int32_t n_slabs, const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
-                 void *__restrict__ slab_val) {
+                 int32_t n_dense_max, int32_t n_slabs, const uint32_t *__restrict__ post_doc,
+                 const void *__restrict__ post_val, void *__restrict__ slab_val) {
     using val_t = typename std::conditional<KIND == B2R_KIND_BM25, double, float>::type;
-    const int h = blockIdx.x;
     const int lane = threadIdx.x & 31, n_warps = (gridDim.y * BLD_THREADS) / 32;
     const int wib = (blockIdx.y * BLD_THREADS + threadIdx.x) >> 5;
     const int sub = tile_docs / B2R_SUBTILES;
     const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
-    const uint32_t *row = dense_ptr + (size_t)h * (n_seg + 1);
-    const int32_t *sid_row = slab_idx + (size_t)h * n_seg;
     const val_t *src = static_cast<const val_t *>(post_val);
     val_t *dst = static_cast<val_t *>(slab_val);
-    for (size_t seg = wib; seg < n_seg; seg += n_warps) {
-        const int32_t sid = sid_row[seg];
-        if (sid < 0 || sid >= n_slabs) continue;
-        const uint32_t lo = row[seg], hi = row[seg + 1];
-        const uint32_t doc0 = (uint32_t)seg * (uint32_t)sub;
-        for (uint32_t p = lo + lane; p < hi; p += 32) {
-            const uint32_t l = post_doc[p] - doc0;
-            if (l < (uint32_t)sub) dst[(size_t)sid * sub + l] = src[p];
+    for (int h = blockIdx.x; h < n_dense_max; h += gridDim.x) {
+        const uint32_t *row = dense_ptr + (size_t)h * (n_seg + 1);
+        const int32_t *sid_row = slab_idx + (size_t)h * n_seg;
+        for (size_t seg = wib; seg < n_seg; seg += n_warps) {
+            const int32_t sid = sid_row[seg];   // (-1 in rows no term owns: the table was preset)
+            if (sid < 0 || sid >= n_slabs) continue;
+            const uint32_t lo = row[seg], hi = row[seg + 1];
+            const uint32_t doc0 = (uint32_t)seg * (uint32_t)sub;
+            for (uint32_t p = lo + lane; p < hi; p += 32) {
+                const uint32_t l = post_doc[p] - doc0;
+                if (l < (uint32_t)sub) dst[(size_t)sid * sub + l] = src[p];
+            }
         }
     }
 }
 
-// share of a sub-tile's documents from which a head-term segment gets a slab (B2R_SLAB_MIN_FRAC overrides it: tuning
-// only; a value above 1 turns slabs off).  Slabs exist for the tile size the scorer has a register layout for.
+// share of a sub-tile's documents from which a segment gets a slab (B2R_SLAB_MIN_FRAC overrides it: tuning only; a
+// value above 1 turns slabs off).  Slabs exist for sub-tiles of >= 256 documents (tile_docs >= B2R_SLAB_TILE_DOCS).
 static uint32_t slab_min_postings(int tile_docs) {
     static const double frac = [] {
         const char *e = getenv("B2R_SLAB_MIN_FRAC");
         const double x = e ? atof(e) : 0.0;
         return x > 0.0 ? x : (double)B2R_SLAB_MIN_NUM / B2R_SLAB_MIN_DEN;
     }();
-    if (tile_docs != B2R_SLAB_TILE_DOCS) return 0xFFFFFFFFu;
+    if (tile_docs < B2R_SLAB_TILE_DOCS) return 0xFFFFFFFFu;
     const double m = frac * (tile_docs / B2R_SUBTILES);
     if (m > (double)(tile_docs / B2R_SUBTILES)) return 0xFFFFFFFFu;
     return m < 1.0 ? 1u : (uint32_t)(m + 0.999999);
@@ -539,7 +541,7 @@ extern "C" int b2r_index_sizes_for(int64_t nnz, int64_t n_docs, int32_t n_vocab,
     out->n_dense_max = nnz / ((int64_t)b2r::dense_min_per_tile() * n_tiles) + 1;
     out->dense_id_bytes = align_up((size_t)n_vocab * 4, 256);
     out->dense_ptr_bytes = align_up((size_t)out->n_dense_max * ((size_t)n_tiles * B2R_SUBTILES + 1) * 4, 256);
-    out->slab_idx_bytes = align_up((size_t)B2R_HEAD_TERMS * (size_t)n_tiles * B2R_SUBTILES * 4, 256);
+    out->slab_idx_bytes = align_up((size_t)out->n_dense_max * (size_t)n_tiles * B2R_SUBTILES * 4, 256);
     return B2R_OK;
 }
 
@@ -661,13 +663,16 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
             }
             B2R_LAUNCH_CHECK();
         }
-        if (ix->slab_idx) {   // number the slab segments of the head rows (values: b2r_index_build_slabs)
+        if (ix->slab_idx) {   // number the slab segments (values: b2r_index_build_slabs)
             int32_t *slab_counter = flag + 2;  // scratch[8..12)
-            B2R_CUDA(cudaMemsetAsync(ix->slab_idx, 0xFF, (size_t)B2R_HEAD_TERMS * ix->n_tiles * B2R_SUBTILES * 4, st));
+            B2R_CUDA(cudaMemsetAsync(ix->slab_idx, 0xFF, (size_t)ix->n_dense_max * ix->n_tiles * B2R_SUBTILES * 4, st));
             const uint32_t slab_min = slab_min_postings(ix->tile_docs);
             if (slab_min != 0xFFFFFFFFu) {
-                slab_mark_kernel<<<B2R_HEAD_TERMS, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->n_tiles, ix->n_dense_max, counter,
-                                                                        slab_min, ix->slab_idx, slab_counter);
+                const dim3 mgrid((unsigned)(ix->n_dense_max < 1024 ? ix->n_dense_max : 1024),
+                                 (unsigned)((ix->n_tiles * B2R_SUBTILES + BLD_THREADS - 1) / BLD_THREADS > 16
+                                                ? 16 : (ix->n_tiles * B2R_SUBTILES + BLD_THREADS - 1) / BLD_THREADS));
+                slab_mark_kernel<<<mgrid, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->n_tiles, ix->n_dense_max, counter, slab_min,
+                                                               ix->slab_idx, slab_counter);
                 B2R_LAUNCH_CHECK();
             }
         }
@@ -695,16 +700,18 @@ extern "C" int b2r_index_build_slabs(const b2r_index *ix, void *stream) {
     B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->dense_id && ix->dense_ptr, "b2r_index_build_slabs: index not built");
     if (ix->n_slabs <= 0) return B2R_OK;
     B2R_CHECK_ARG(ix->slab_idx && ix->slab_val, "b2r_index_build_slabs: slab buffers not set");
-    B2R_CHECK_ARG(ix->tile_docs == B2R_SLAB_TILE_DOCS, "b2r_index_build_slabs: no slabs for tile_docs=%d", ix->tile_docs);
+    B2R_CHECK_ARG(ix->tile_docs >= B2R_SLAB_TILE_DOCS, "b2r_index_build_slabs: no slabs for tile_docs=%d", ix->tile_docs);
     B2R_CUDA(cudaMemsetAsync(ix->slab_val, 0, b2r_index_slab_bytes(ix->n_slabs, ix->tile_docs, ix->kind), st));
     // (rows beyond the number of dense terms hold no slab: slab_idx is -1 there)
-    const dim3 grid(B2R_HEAD_TERMS, 32);
+    const dim3 grid((unsigned)(ix->n_dense_max < 2048 ? ix->n_dense_max : 2048), 4);
     if (ix->kind == B2R_KIND_BM25)
         slab_fill_kernel<B2R_KIND_BM25><<<grid, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->slab_idx, ix->n_tiles, ix->tile_docs,
-                                                                      ix->n_slabs, ix->post_doc, ix->post_val, ix->slab_val);
+                                                                      ix->n_dense_max, ix->n_slabs, ix->post_doc,
+                                                                      ix->post_val, ix->slab_val);
     else
         slab_fill_kernel<B2R_KIND_IMPACT><<<grid, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->slab_idx, ix->n_tiles, ix->tile_docs,
-                                                                        ix->n_slabs, ix->post_doc, ix->post_val, ix->slab_val);
+                                                                        ix->n_dense_max, ix->n_slabs, ix->post_doc,
+                                                                        ix->post_val, ix->slab_val);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }

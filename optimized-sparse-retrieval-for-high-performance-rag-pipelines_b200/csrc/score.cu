@@ -55,6 +55,10 @@ __device__ __forceinline__ float2 ld_stream_v2f32(const float2 *p) {
 
 constexpr int SC_THREADS = 32 * B2R_SUBTILES;  // one warp per sub-tile of the CTA's doc tile
 
+// The accumulators are cleared by the copy engine (cp.async.bulk from this zero page), not by stores:
+// the LSU / shared-memory data pipe is the scorer's bottleneck and the bulk copy does not go through it.
+__device__ __align__(128) double g_zero_page[16384 / B2R_SUBTILES];  // one sub-tile of the largest tile
+
 __device__ __forceinline__ uint32_t sc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sc_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -104,65 +108,100 @@ struct TermW<B2R_KIND_BM25> {
 };
 #endif
 
-// One DENSE (non-slab) term applied by one warp to its own sub-tile: [beg, end) are exactly the warp's postings.
+// One term applied by one warp to its own sub-tile.  dense: [beg, end) are exactly the warp's postings;
+// otherwise [beg, end) is the tile's (small) block and the warp keeps the postings of its doc range.
 template <int KIND, bool FIRST>
-__device__ __forceinline__ void apply_dense_term(uint32_t beg, uint32_t end, int lane, uint32_t my_doc0,
-                                                 const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
-                                                 double *acc_w, typename TermW<KIND>::type w_idf_t,
-                                                 typename TermW<KIND>::type w_q_t) {
-    // BM25 multiplies in f64: the widening is done once per term and warp (f32 -> f64 conversions run on a slow pipe)
+__device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end, int lane, int sub, uint32_t my_doc0,
+                                           const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
+                                           double *acc_w, typename TermW<KIND>::type w_idf_t,
+                                           typename TermW<KIND>::type w_q_t) {
+    // BM25 multiplies in f64: the widening was done ONCE per lane when the query was staged (f32 -> f64 conversions
+    // run on a slow pipe, and this function is entered once per term, warp and tile)
     const double w_idf64 = (double)w_idf_t, w_q64 = (double)w_q_t;
     const float w_idf = (float)w_idf_t, w_q = (float)w_q_t;  // (exact: the values are f32 numbers)
-    uint32_t p = beg + lane;
-    for (; p + 96 < end; p += 128) {  // 4 independent postings in flight per lane
-        uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + 32);
-        uint32_t d2 = ld_stream_u32(post_doc + p + 64), d3 = ld_stream_u32(post_doc + p + 96);
-        double u0 = load_val<KIND>(post_val, p), u1 = load_val<KIND>(post_val, p + 32);
-        double u2 = load_val<KIND>(post_val, p + 64), u3 = load_val<KIND>(post_val, p + 96);
-        apply_posting<KIND, FIRST>(acc_w, d0 - my_doc0, u0, w_idf, w_q, w_idf64, w_q64);
-        apply_posting<KIND, FIRST>(acc_w, d1 - my_doc0, u1, w_idf, w_q, w_idf64, w_q64);
-        apply_posting<KIND, FIRST>(acc_w, d2 - my_doc0, u2, w_idf, w_q, w_idf64, w_q64);
-        apply_posting<KIND, FIRST>(acc_w, d3 - my_doc0, u3, w_idf, w_q, w_idf64, w_q64);
-    }
-    for (; p < end; p += 32) {
-        uint32_t d = ld_stream_u32(post_doc + p);
-        double u = load_val<KIND>(post_val, p);
-        apply_posting<KIND, FIRST>(acc_w, d - my_doc0, u, w_idf, w_q, w_idf64, w_q64);
+    if (dense) {
+        uint32_t p = beg + lane;
+        for (; p + 96 < end; p += 128) {  // 4 independent postings in flight per lane
+            uint32_t d0 = ld_stream_u32(post_doc + p), d1 = ld_stream_u32(post_doc + p + 32);
+            uint32_t d2 = ld_stream_u32(post_doc + p + 64), d3 = ld_stream_u32(post_doc + p + 96);
+            double u0 = load_val<KIND>(post_val, p), u1 = load_val<KIND>(post_val, p + 32);
+            double u2 = load_val<KIND>(post_val, p + 64), u3 = load_val<KIND>(post_val, p + 96);
+            apply_posting<KIND, FIRST>(acc_w, d0 - my_doc0, u0, w_idf, w_q, w_idf64, w_q64);
+            apply_posting<KIND, FIRST>(acc_w, d1 - my_doc0, u1, w_idf, w_q, w_idf64, w_q64);
+            apply_posting<KIND, FIRST>(acc_w, d2 - my_doc0, u2, w_idf, w_q, w_idf64, w_q64);
+            apply_posting<KIND, FIRST>(acc_w, d3 - my_doc0, u3, w_idf, w_q, w_idf64, w_q64);
+        }
+        for (; p < end; p += 32) {
+            uint32_t d = ld_stream_u32(post_doc + p);
+            double u = load_val<KIND>(post_val, p);
+            apply_posting<KIND, FIRST>(acc_w, d - my_doc0, u, w_idf, w_q, w_idf64, w_q64);
+        }
+    } else {
+        for (uint32_t p = beg + lane; p < end; p += 32) {
+            const uint32_t rel = __ldg(post_doc + p) - my_doc0;  // blocks are shared by the 8 warps: keep in L1
+            if (rel < (uint32_t)sub) {
+                double u = load_val<KIND>(post_val, p);
+                apply_posting<KIND, FIRST>(acc_w, rel, u, w_idf, w_q, w_idf64, w_q64);
+            }
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// The scorer: TILE-STATIONARY.  One CTA = one doc tile x a range of queries; it first copies the tile's head-term
-// slabs (include/b200ret.h: the sub-tile's posting values in document order, 0 = no posting) into shared memory --
-// once per CTA, i.e. once per (tile, query range) instead of once per (tile, query) -- and then its warps walk the
-// queries of the range.  A warp owns one sub-tile of tile_docs/8 documents of one QUERY SLOT (a CTA runs up to
-// four queries side by side, 8 warps each); warps never synchronise with each other after the slab copy.
-// Per (query, sub-tile) the warp applies the query's terms in ascending term id (the reference's summation order:
-// CSR rows are sorted by term id), each term in one of three ways:
-//   slab    the term is a head term and its segment of this sub-tile has a slab: lane l owns documents
-//           {64 c + 2 l, 64 c + 2 l + 1} and keeps their accumulators in REGISTERS; a posting costs one 8-byte
-//           shared-memory read and three f64 operations -- no document id, no read-modify-write, no L2 traffic.
-//           r += (idf * 0) * q leaves r bit-identical (r is never -0.0: it starts at +0.0), so absent documents
-//           need no mask; terms with a non-finite weight never take this path.
-//   dense   the term has sub-tile offsets (dense_ptr): the warp streams its own bank-scheduled segment from L2 and
-//           does read-modify-write on the sub-tile's accumulators in shared memory;
-//   sparse  every warp scans the tile's small block and keeps the postings of its own doc range.
-// The accumulators move between registers and shared memory only when they have to: a run of slab terms stays in
-// registers, a sparse block without a posting in the warp's doc range does not disturb them, and a sub-tile whose
-// last applied term was a slab runs its epilogue straight from the registers.  Shared-memory accumulators are
-// zero-filled lazily (only sub-tiles that see a non-slab posting ever need them).
-// Why: with one CTA per (query, tile) every query re-fetched the head terms' postings from L2 (26 GB of L2->SM
-// traffic per 1024-query step against ~12 TB/s of fabric: the round-1 kernel's real bound).
+// A slab (include/b200ret.h, b2r_index): the sub-tile's posting values in document order, 0 where the document has
+// no posting.  Lane l handles documents {64 c + 2 l, 64 c + 2 l + 1}: one coalesced 16-byte load brings two values,
+// the accumulators are read and written 16 bytes at a time (conflict-free by construction) and no document id is
+// loaded at all -- about 5 instructions per 32 documents where the posting loop above needs about 24.
+// acc += (idf * 0) * q leaves acc bit-identical (acc is never -0.0: it starts at +0.0), so absent documents need no
+// mask; terms with a non-finite weight never take this path (see the staging code).  FIRST: the sub-tile has not
+// been touched (and not been cleared): every accumulator is written.
+#ifndef SC_SLAB_BATCH
+#define SC_SLAB_BATCH 4   // 16-byte slab loads in flight per lane
+#endif
+template <int KIND, bool FIRST>
+__device__ __forceinline__ void apply_slab(double *acc_w, const void *__restrict__ slab_val, int32_t slab, int sub, int lane,
+                                           float w_idf, float w_q) {
+    double *a_l = acc_w + 2 * lane;
+    if (KIND == B2R_KIND_BM25) {
+        const double2 *sv = static_cast<const double2 *>(slab_val) + (size_t)slab * (size_t)(sub >> 1) + lane;
+        const double wi = (double)w_idf, wq = (double)w_q;
+        for (int c0 = 0; c0 < (sub >> 6); c0 += SC_SLAB_BATCH) {   // (slabs exist for sub-tiles of >= 256 documents)
+            double2 u[SC_SLAB_BATCH];
+#pragma unroll
+            for (int c = 0; c < SC_SLAB_BATCH; ++c) u[c] = ld_stream_v2f64(sv + 32 * (c0 + c));
+#pragma unroll
+            for (int c = 0; c < SC_SLAB_BATCH; ++c) {
+                double2 a = FIRST ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(a_l + 64 * (c0 + c));
+                a.x = __dadd_rn(a.x, __dmul_rn(__dmul_rn(wi, u[c].x), wq));
+                a.y = __dadd_rn(a.y, __dmul_rn(__dmul_rn(wi, u[c].y), wq));
+                *reinterpret_cast<double2 *>(a_l + 64 * (c0 + c)) = a;
+            }
+        }
+    } else {
+        const float2 *sv = static_cast<const float2 *>(slab_val) + (size_t)slab * (size_t)(sub >> 1) + lane;
+        for (int c0 = 0; c0 < (sub >> 6); c0 += SC_SLAB_BATCH) {
+            float2 u[SC_SLAB_BATCH];
+#pragma unroll
+            for (int c = 0; c < SC_SLAB_BATCH; ++c) u[c] = ld_stream_v2f32(sv + 32 * (c0 + c));
+#pragma unroll
+            for (int c = 0; c < SC_SLAB_BATCH; ++c) {
+                double2 a = FIRST ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(a_l + 64 * (c0 + c));
+                // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens
+                a.x = __dadd_rn(a.x, (double)__fmul_rn(__fmul_rn(u[c].x, w_q), w_idf));
+                a.y = __dadd_rn(a.y, (double)__fmul_rn(__fmul_rn(u[c].y, w_q), w_idf));
+                *reinterpret_cast<double2 *>(a_l + 64 * (c0 + c)) = a;
+            }
+        }
+    }
+}
+
+// One CTA = one (query, doc tile); one WARP = one sub-tile of tile_docs/8 docs whose f64 accumulators
+// it alone touches.  A warp applies the query's terms in ascending term id to its own sub-tile, so the
+// only synchronisation is __syncwarp: no CTA barrier, no atomics, no load imbalance between warps
+// (a dense term's postings are split by sub-tile through dense_ptr; a sparse term's small block is
+// scanned by every warp, each keeping the postings that fall in its range).
 enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1, SC_OUT_MAXIMA = 2 };
 enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1 };
 constexpr int SC_GROUPS_PER_TILE = 32 * B2R_SUBTILES;  // MAXIMA: one group maximum per lane
-#ifndef SC_MAX_SLOTS_DEF
-#define SC_MAX_SLOTS_DEF 4
-#endif
-constexpr int SC_MAX_SLOTS = SC_MAX_SLOTS_DEF;         // queries a CTA works on side by side
-constexpr int SC_REC_CAP = 2048;                       // term records of a CTA's query range staged in shared memory
-constexpr int SC_SLAB_SUB = B2R_SLAB_TILE_DOCS / B2R_SUBTILES;   // 256 documents per slab
-constexpr int SC_SLAB_PAIRS = SC_SLAB_SUB / 64;        // double2 accumulators per lane in the register layout
 
 struct ScoreOut {
     // DENSE: scores[queries, scores_stride], column = out_tile * tile_docs + doc in tile
@@ -180,631 +219,204 @@ struct ScoreOut {
     uint32_t doc_id_base;
 };
 
-template <int KIND, int OUT, bool SLABS>
-__global__ void __launch_bounds__(SC_MAX_SLOTS * SC_THREADS, 1)
+template <int KIND, int OUT>
+#ifndef SC_MIN_CTAS
+#define SC_MIN_CTAS 5  // 6 CTAs/SM is what 32 KB of accumulators per CTA allows (40 registers per thread)
+#endif
+__global__ void __launch_bounds__(SC_THREADS, SC_MIN_CTAS)
 score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
                    const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
                    const uint32_t *__restrict__ dense_ptr, const int32_t *__restrict__ slab_idx,
-                   const void *__restrict__ slab_val, int n_slabs, int n_tiles, int tile_docs,
+                   const void *__restrict__ slab_val, int n_tiles, int tile_docs,
                    const int32_t *__restrict__ q_ptr, const int32_t *__restrict__ q_terms,
-                   const float *__restrict__ q_weights, const float *__restrict__ idf, int q0, int nq, int range_len,
-                   int tile_mode, int tile_step, int diag, ScoreOut o) {
-    using val_t = typename std::conditional<KIND == B2R_KIND_BM25, double, float>::type;
-    using val2_t = typename std::conditional<KIND == B2R_KIND_BM25, double2, float2>::type;
-    extern __shared__ __align__(128) unsigned char sc_smem[];
-    __shared__ __align__(8) uint64_t cbar;              // "the slabs of this tile have landed"
-    __shared__ int cache_ok[B2R_HEAD_TERMS * B2R_SUBTILES];
+                   const float *__restrict__ q_weights, const float *__restrict__ idf, int q0, int tile_mode,
+                   int tile_step, int n_y, ScoreOut o) {
+    extern __shared__ double acc[];  // [tile_docs]
+    __shared__ __align__(8) uint64_t zbar[B2R_SUBTILES];  // per warp: "my accumulators have been cleared"
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slots = blockDim.x / SC_THREADS;
-    const int slot = warp / B2R_SUBTILES, w = warp % B2R_SUBTILES;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ql = blockIdx.x;  // query index inside this launch's chunk
+    const int q = q0 + ql;
+    if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap) return;
     const int sub = tile_docs / B2R_SUBTILES;
-    const int y = blockIdx.y;
-    const int tile = tile_mode == SC_TILES_ALL ? y : y * tile_step;
+    double *acc_w = acc + w * sub;
     const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
     const size_t dense_row = n_seg + 1;
-    const int r0 = blockIdx.x * range_len, r1 = min(nq, r0 + range_len);
-    // layout: accumulators f64[slots][tile_docs], (SLABS) the slab cache val_t[B2R_HEAD_TERMS][tile_docs], then the
-    // term records of the CTA's query range int4[SC_REC_CAP] = {idf, query weight, term id, dense row}
-    double *acc_w = reinterpret_cast<double *>(sc_smem) + (size_t)slot * tile_docs + (size_t)w * sub;
-    const val_t *cache = reinterpret_cast<const val_t *>(sc_smem + (size_t)slots * tile_docs * sizeof(double));
-    int4 *rec = reinterpret_cast<int4 *>(sc_smem + (size_t)slots * tile_docs * sizeof(double) +
-                                         (SLABS ? (size_t)B2R_HEAD_TERMS * tile_docs * sizeof(val_t) : 0));
-
-    if (OUT == SC_OUT_DENSE && o.gate != nullptr) {   // a gated launch is expected to find nothing to do
-        int any = 0;
-        for (int ql = r0 + (int)threadIdx.x; ql < r1; ql += blockDim.x) any |= o.gate[ql] > o.gate_cap;
-        if (!__syncthreads_or(any)) return;
-    }
-    // The term records of the range are staged ONCE per CTA (every (query, sub-tile) task would otherwise walk the
-    // dependent chain q_terms -> idf / dense_id on its own, four exposed L2 latencies per task).
-    const int tbase = q_ptr[q0 + r0];
-    {
-        const int n_rec = min(q_ptr[q0 + r1] - tbase, SC_REC_CAP);
-        for (int i = threadIdx.x; i < n_rec; i += blockDim.x) {
-            const int t = q_terms[tbase + i];
-            rec[i] = make_int4(__float_as_int(idf[t]), __float_as_int(q_weights[tbase + i]), t, dense_id[t]);
-        }
-    }
-    if (!SLABS) __syncthreads();
-    if (SLABS) {
-        const uint32_t cbar_a = sc_smem_u32(&cbar);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cbar_a) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t bytes = 0;
-            for (int i = lane; i < B2R_HEAD_TERMS * B2R_SUBTILES; i += 32) {
-                const int h = i / B2R_SUBTILES, sseg = i % B2R_SUBTILES;
-                const int32_t sid = slab_idx[(size_t)h * n_seg + (size_t)tile * B2R_SUBTILES + sseg];
-                const int ok = sid >= 0 && sid < n_slabs;
-                cache_ok[i] = ok;
-                if (ok) {
-                    const uint32_t nb = (uint32_t)(SC_SLAB_SUB * sizeof(val_t));
-                    asm volatile(
-                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                            sc_smem_u32(cache + (size_t)h * tile_docs + (size_t)sseg * SC_SLAB_SUB)),
-                        "l"(static_cast<const val_t *>(slab_val) + (size_t)sid * SC_SLAB_SUB), "r"(nb), "r"(cbar_a)
-                        : "memory");
-                    bytes += nb;
-                }
-            }
-#pragma unroll
-            for (int ofs = 16; ofs; ofs >>= 1) bytes += __shfl_xor_sync(full, bytes, ofs);
-            // (a copy that completes before this arrive only drives the transaction count negative for a moment:
-            // the phase cannot complete before the one pending arrival below)
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cbar_a), "r"(bytes) : "memory");
-        }
-        __syncthreads();                 // cache_ok is visible
-        sc_mbar_wait(cbar_a, 0);         // the slab bytes are visible
-    }
-
-    auto load_rec = [&](int j) -> int4 {   // record of term j (index into q_terms)
-        if (j - tbase < SC_REC_CAP) return rec[j - tbase];
-        const int t = q_terms[j];
-        return make_int4(__float_as_int(idf[t]), __float_as_int(q_weights[j]), t, dense_id[t]);
-    };
-    auto offsets_of = [&](const int4 rc, uint32_t &beg, uint32_t &end) {   // postings of the term in my sub-tile / tile
-        if (rc.w >= 0) {
-            const uint32_t *row = dense_ptr + (size_t)rc.w * dense_row + (size_t)tile * B2R_SUBTILES + w;
-            beg = row[0];
-            end = row[1];
-        } else {
-            const size_t e = (size_t)rc.z * n_tiles + tile;
-            beg = blk_ptr[e];
-            end = blk_ptr[e + 1];
-        }
-    };
-    // software pipeline over the warp's queries: the offsets of the NEXT query's (first 32) terms and the q_ptr pair of
-    // the one after it are in flight while the current query is applied
-    int qs = 0, qe = 0, nqs = 0, nqe = 0;
-    uint32_t pbeg = 0, pend = 0;
-    if (r0 + slot < r1) {
-        qs = q_ptr[q0 + r0 + slot];
-        qe = q_ptr[q0 + r0 + slot + 1];
-        if (lane < min(32, qe - qs)) offsets_of(load_rec(qs + lane), pbeg, pend);
-    }
-    if (r0 + slot + slots < r1) {
-        nqs = q_ptr[q0 + r0 + slot + slots];
-        nqe = q_ptr[q0 + r0 + slot + slots + 1];
-    }
-    for (int ql = r0 + slot; ql < r1; ql += slots) {
-        uint32_t nbeg = 0, nend = 0;
-        int nnqs = 0, nnqe = 0;
-        if (ql + slots < r1 && lane < min(32, nqe - nqs)) offsets_of(load_rec(nqs + lane), nbeg, nend);
-        if (ql + 2 * slots < r1) {
-            nnqs = q_ptr[q0 + ql + 2 * slots];
-            nnqe = q_ptr[q0 + ql + 2 * slots + 1];
-        }
-        if (!(OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap)) {
-        const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
-        // FUSED: the candidate threshold of this query
-        uint64_t thr = 0;
-        double thr_lo = 0.0;
-        if (OUT == SC_OUT_FUSED) {
-            thr = o.thr_keys[ql];
-            const uint32_t thr_hi = (uint32_t)(thr >> 32);
-            // A document can only beat thr if f32(acc) >= the threshold score.  Instead of converting all
-            // accumulators of the tile, they are compared in f64 against the f32 value just below the threshold
-            // score: acc < pred(thr_f) implies f32(acc) <= pred(thr_f) < thr_f (rounding is monotone).  Only
-            // survivors are converted and keyed.  thr_hi == 0: no threshold yet.
-            // ordered encoding: -1 = next smaller f32; 0x7fffffff would be -0.0 (== +0.0 in the ranking): skip it;
-            // at or below -inf (0x007fffff) there is nothing smaller: no filter
-            uint32_t thr_ord = thr_hi > 0x007fffffu ? thr_hi - 1u : 0u;
-            if (thr_ord == 0x7fffffffu) thr_ord = 0x7ffffffeu;
-            thr_lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
-            // "strictly positive scores only" (kth_of_maxima's positive floor): nothing below 2^-150 rounds to a
-            // positive f32, so the untouched documents (acc == 0) never reach the conversion path
-            if (thr == ((0x80000000ull << 32) | 0xFFFFFFFFull)) thr_lo = __longlong_as_double(0x3690000000000000ll);
-        }
-
-        // where the sub-tile's accumulators are (warp-uniform): nowhere yet (all +0.0), registers, or shared memory
-        bool first = true;   // no term has touched this sub-tile yet
-        bool in_reg = false;
-        double2 r[SC_SLAB_PAIRS];
-        auto to_smem = [&]() {  // make shared memory hold the accumulators
-            if (SLABS && in_reg) {
-#pragma unroll
-                for (int c = 0; c < SC_SLAB_PAIRS; ++c) *reinterpret_cast<double2 *>(acc_w + 64 * c + 2 * lane) = r[c];
-                in_reg = false;
-                __syncwarp();
-            } else if (first) {
-                for (int i = lane * 2; i < sub; i += 64) *reinterpret_cast<double2 *>(acc_w + i) = make_double2(0.0, 0.0);
-                __syncwarp();
-            }
-        };
-
-        for (int j0 = qs; j0 < qe; j0 += 32) {
-            const int nt = min(32, qe - j0);
-            // lane j stages term j0 + j for this (tile, sub-tile); the offsets of the first 32 terms were prefetched
-            uint32_t my_beg = 0, my_end = 0;
-            int my_kind = 0;   // 0 sparse, 1 dense, 2 + h: slab of head row h
-            typename TermW<KIND>::type my_idf = 0, my_qw = 0;
-            if (lane < nt) {
-                const int4 rc = load_rec(j0 + lane);
-                my_idf = __int_as_float(rc.x);
-                my_qw = __int_as_float(rc.y);
-                if (j0 == qs) {
-                    my_beg = pbeg;
-                    my_end = pend;
-                } else {
-                    offsets_of(rc, my_beg, my_end);
-                }
-                if (rc.w >= 0) {
-                    my_kind = 1;
-                    // slabs add (idf * 0) * q for absent documents: only exact when both weights are finite
-                    if (SLABS && rc.w < B2R_HEAD_TERMS && cache_ok[rc.w * B2R_SUBTILES + w] && isfinite((float)my_idf) &&
-                        isfinite((float)my_qw))
-                        my_kind = 2 + rc.w;
-                }
-            }
-            for (int j = 0; j < nt; ++j) {
-                const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
-                if (beg == end) continue;  // warp-uniform
-                const typename TermW<KIND>::type w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
-                const int kind = __shfl_sync(full, my_kind, j);
-                if (diag && kind == 0) continue;   // B2R_SCORE_DIAG=1: measurement only (sparse terms skipped: wrong results)
-                if (SLABS && kind >= 2) {
-                    if (!in_reg) {
-                        if (first) {
-#pragma unroll
-                            for (int c = 0; c < SC_SLAB_PAIRS; ++c) r[c] = make_double2(0.0, 0.0);
-                        } else {  // (shared memory was written under __syncwarp)
-#pragma unroll
-                            for (int c = 0; c < SC_SLAB_PAIRS; ++c)
-                                r[c] = *reinterpret_cast<const double2 *>(acc_w + 64 * c + 2 * lane);
-                        }
-                        in_reg = true;
-                    }
-                    const val2_t *cv = reinterpret_cast<const val2_t *>(cache + (size_t)(kind - 2) * tile_docs +
-                                                                        (size_t)w * SC_SLAB_SUB) + lane;
-                    if (KIND == B2R_KIND_BM25) {
-                        const double wi = (double)w_idf, wq = (double)w_q;
-#pragma unroll
-                        for (int c = 0; c < SC_SLAB_PAIRS; ++c) {
-                            const val2_t u = cv[32 * c];
-                            r[c].x = __dadd_rn(r[c].x, __dmul_rn(__dmul_rn(wi, (double)u.x), wq));
-                            r[c].y = __dadd_rn(r[c].y, __dmul_rn(__dmul_rn(wi, (double)u.y), wq));
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < SC_SLAB_PAIRS; ++c) {
-                            const val2_t u = cv[32 * c];
-                            // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens
-                            r[c].x = __dadd_rn(r[c].x, (double)__fmul_rn(__fmul_rn((float)u.x, (float)w_q), (float)w_idf));
-                            r[c].y = __dadd_rn(r[c].y, (double)__fmul_rn(__fmul_rn((float)u.y, (float)w_q), (float)w_idf));
-                        }
-                    }
-                    first = false;
-                    continue;
-                }
-                if (kind != 0) {
-                    const bool was_first = first;
-                    to_smem();
-                    if (was_first) apply_dense_term<KIND, true>(beg, end, lane, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
-                    else apply_dense_term<KIND, false>(beg, end, lane, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
-                    first = false;
-                    __syncwarp();
-                } else {
-                    // sparse term: the tile's block is shared by the 8 warps of every slot (kept in L1); a block with
-                    // no posting in this warp's doc range leaves the accumulators where they are
-                    const double w_idf64 = (double)w_idf, w_q64 = (double)w_q;
-                    bool touched = false;
-                    for (uint32_t p0 = beg; p0 < end; p0 += 32) {
-                        const uint32_t p = p0 + lane;
-                        const uint32_t rel = p < end ? __ldg(post_doc + p) - my_doc0 : 0xFFFFFFFFu;
-                        const bool hit = rel < (uint32_t)sub;
-                        if (!__any_sync(full, hit)) continue;
-                        if (!touched) to_smem();
-                        if (hit) {
-                            const double u = load_val<KIND>(post_val, p);
-                            apply_posting<KIND, false>(acc_w, rel, u, (float)w_idf, (float)w_q, w_idf64, w_q64);
-                        }
-                        touched = true;
-                        first = false;
-                    }
-                    if (touched) __syncwarp();
-                }
-            }
-        }
-
-        // ---- epilogue over the sub-tile's accumulators: pair (i, i + 1), i = 64 c + 2 lane
-        double m = -__longlong_as_double(0x7ff0000000000000ll);
-        float *out_row = nullptr;
-        if (OUT == SC_OUT_DENSE) out_row = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * tile_docs + w * sub;
-        auto emit = [&](const double2 a, const int i) {
-            if (OUT == SC_OUT_DENSE) {
-                *reinterpret_cast<float2 *>(out_row + i) = make_float2(__double2float_rn(a.x), __double2float_rn(a.y));
-            } else if (OUT == SC_OUT_MAXIMA) {
-                // one maximum per lane over the (valid) documents it reads; f32(max) == max(f32): rounding is monotone
-                const uint32_t doc = my_doc0 + i;
-                if (doc < o.n_docs) m = fmax(m, a.x);
-                if (doc + 1 < o.n_docs) m = fmax(m, a.y);
-            } else {
-                if (a.x >= thr_lo || a.y >= thr_lo) {
-                    const double av[2] = {a.x, a.y};
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint32_t doc = my_doc0 + i + c;
-                        if (av[c] >= thr_lo && doc < o.n_docs) {
-                            const uint64_t key = make_key(ord_f32(__double2float_rn(av[c])), o.doc_id_base + doc);
-                            if (key > thr) {
-                                const int slot_c = atomicAdd(o.cand_cnt + ql, 1);
-                                if (slot_c < o.cap) o.cand[(int64_t)ql * o.cap + slot_c] = key;
-                            }
-                        }
-                    }
-                }
-            }
-        };
-        if (SLABS && in_reg) {
-#pragma unroll
-            for (int c = 0; c < SC_SLAB_PAIRS; ++c) emit(r[c], 64 * c + 2 * lane);
-        } else if (first) {   // no posting of the query in this sub-tile: every score is +0.0
-            for (int i = lane * 2; i < sub; i += 64) emit(make_double2(0.0, 0.0), i);
-        } else {
-            for (int i = lane * 2; i < sub; i += 64) emit(*reinterpret_cast<const double2 *>(acc_w + i), i);
-        }
-        if (OUT == SC_OUT_MAXIMA)
-            o.scores[(int64_t)ql * o.scores_stride + (int64_t)y * SC_GROUPS_PER_TILE + w * 32 + lane] = __double2float_rn(m);
-        __syncwarp();   // the next query's writes must not overtake this epilogue's reads
-        }  // (gate)
-        qs = nqs;
-        qe = nqe;
-        nqs = nnqs;
-        nqe = nnqe;
-        pbeg = nbeg;
-        pend = nend;
-    }  // query loop
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// The scorer for tile_docs == B2R_SLAB_TILE_DOCS (the default layout): same tile-stationary scheme as above, written
-// for instruction count -- the round-1 kernel and the generic kernel above spend most of their issue slots on per-
-// (query, sub-tile) overhead (term staging, shuffles, threshold set-up), not on postings.  Here everything that does
-// not depend on the warp is computed ONCE per CTA and chunk of queries and kept in shared memory:
-//   rec[i]  one 16-byte record per query term {idf, query weight, first posting, kind word}, in term order
-//           kind word: [7:0] 0 sparse / 1 dense / 2 + h head row h; [15:8] sub-tile mask (sparse: sub-tiles of this
-//           tile that hold a posting of the term; head: sub-tiles whose segment has a slab); [31:16] sparse: postings
-//           of the term in this tile
-//   cum[i]  dense and head terms: the 9 sub-tile offsets of the term's postings in this tile, relative, u16
-//   qthr[q] FUSED: the query's candidate threshold as a key and as the f64 bound the accumulators are compared with
-// A (query, sub-tile) task is then a loop over records read by broadcast loads: no shuffles, no global loads before
-// the postings themselves, all loop bounds constant.  A sparse term whose block has no posting in the warp's
-// sub-tile costs one record load and a bit test.
-constexpr int T2K_TILE = B2R_SLAB_TILE_DOCS;
-constexpr int T2K_SUB = T2K_TILE / B2R_SUBTILES;        // 256 documents per warp
-constexpr int T2K_PAIRS = T2K_SUB / 64;                 // double2 accumulators per lane
-constexpr int T2K_SLOTS = 4;
-constexpr int T2K_REC_CAP = 704;                        // term records per chunk of queries
-constexpr int T2K_Q_CAP = 128;                          // queries per chunk
-constexpr int T2K_CUM = 10;                             // u16 per record in cum[] (9 used)
-static_assert(T2K_PAIRS == SC_SLAB_PAIRS && T2K_SUB == SC_SLAB_SUB, "slab layout");
-
-struct __align__(16) T2KRec {
-    float idf, w;
-    uint32_t base, kind;
-};
-struct __align__(16) T2KThr {
-    uint64_t thr;
-    double lo;
-};
-
-template <int KIND>
-constexpr size_t t2k_smem_bytes() {
-    return (size_t)T2K_SLOTS * T2K_TILE * 8 + (size_t)B2R_HEAD_TERMS * T2K_TILE * (KIND == B2R_KIND_BM25 ? 8 : 4) +
-           (size_t)T2K_REC_CAP * sizeof(T2KRec) + (size_t)T2K_REC_CAP * T2K_CUM * 2 + (size_t)(T2K_Q_CAP + 4) * 4 +
-           (size_t)T2K_Q_CAP * sizeof(T2KThr);
-}
-
-// record of query term j for doc tile `tile` (see above); okm[h] = sub-tiles of this tile in which head row h has a slab
-__device__ __forceinline__ T2KRec t2k_make_record(int j, int tile, int n_tiles, const int32_t *__restrict__ q_terms,
-                                                  const float *__restrict__ q_weights, const float *__restrict__ idf,
-                                                  const int32_t *__restrict__ dense_id, const uint32_t *__restrict__ dense_ptr,
-                                                  const uint32_t *__restrict__ blk_ptr, const uint32_t *__restrict__ post_doc,
-                                                  const int *okm, bool slabs, uint16_t *cum_out) {
-    T2KRec rc;
-    const int t = q_terms[j];
-    rc.w = q_weights[j];
-    rc.idf = idf[t];
-    const int32_t did = dense_id[t];
-    if (did >= 0) {
-        const uint32_t *row = dense_ptr + (size_t)did * ((size_t)n_tiles * B2R_SUBTILES + 1) + (size_t)tile * B2R_SUBTILES;
-        const uint32_t o0 = row[0];
-        cum_out[0] = 0;
-#pragma unroll
-        for (int sg = 1; sg <= B2R_SUBTILES; ++sg) cum_out[sg] = (uint16_t)(row[sg] - o0);
-        rc.base = o0;
-        rc.kind = 1;
-        // slabs add (idf * 0) * q for absent documents: only exact when both weights are finite
-        if (slabs && did < B2R_HEAD_TERMS && isfinite(rc.idf) && isfinite(rc.w)) rc.kind = (2u + did) | ((uint32_t)okm[did] << 8);
-    } else {
-        const size_t e = (size_t)t * n_tiles + tile;
-        const uint32_t beg = blk_ptr[e], n = blk_ptr[e + 1] - beg;
-        uint32_t mask = n > 16 ? 0xFFu : 0u;
-        if (n <= 16)
-            for (uint32_t p = 0; p < n; ++p) mask |= 1u << (((post_doc[beg + p] - (uint32_t)tile * T2K_TILE) / T2K_SUB) & 7);
-        rc.base = beg;
-        rc.kind = (mask << 8) | (n << 16);
-    }
-    return rc;
-}
-
-template <int KIND, int OUT>
-__global__ void __launch_bounds__(T2K_SLOTS * SC_THREADS, 1)
-score_t2k_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
-                 const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
-                 const uint32_t *__restrict__ dense_ptr, const int32_t *__restrict__ slab_idx,
-                 const void *__restrict__ slab_val, int n_slabs, int n_tiles, const int32_t *__restrict__ q_ptr,
-                 const int32_t *__restrict__ q_terms, const float *__restrict__ q_weights, const float *__restrict__ idf,
-                 int q0, int nq, int range_len, int tile_mode, int tile_step, ScoreOut o) {
-    using val_t = typename std::conditional<KIND == B2R_KIND_BM25, double, float>::type;
-    using val2_t = typename std::conditional<KIND == B2R_KIND_BM25, double2, float2>::type;
-    extern __shared__ __align__(128) unsigned char sc_smem[];
-    __shared__ __align__(8) uint64_t cbar;   // "the slabs of this tile have landed"
-    __shared__ int okm[B2R_HEAD_TERMS];      // per head row: sub-tiles of this tile whose segment has a slab
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = warp / B2R_SUBTILES, w = warp % B2R_SUBTILES;
-    const int y = blockIdx.y;
-    const int tile = tile_mode == SC_TILES_ALL ? y : y * tile_step;
-    const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
-    const int r0 = blockIdx.x * range_len, r1 = min(nq, r0 + range_len);
-    const bool slabs = slab_idx != nullptr && n_slabs > 0;
-
-    double *acc_w = reinterpret_cast<double *>(sc_smem) + (size_t)slot * T2K_TILE + (size_t)w * T2K_SUB;
-    unsigned char *sp = sc_smem + (size_t)T2K_SLOTS * T2K_TILE * 8;
-    const val_t *cache = reinterpret_cast<const val_t *>(sp);
-    sp += (size_t)B2R_HEAD_TERMS * T2K_TILE * sizeof(val_t);
-    T2KRec *rec = reinterpret_cast<T2KRec *>(sp);
-    sp += (size_t)T2K_REC_CAP * sizeof(T2KRec);
-    uint16_t *cum = reinterpret_cast<uint16_t *>(sp);
-    sp += (size_t)T2K_REC_CAP * T2K_CUM * 2;
-    int *qoff = reinterpret_cast<int *>(sp);
-    sp += (size_t)(T2K_Q_CAP + 4) * 4;
-    T2KThr *qthr = reinterpret_cast<T2KThr *>(sp);
-
-    if (OUT == SC_OUT_DENSE && o.gate != nullptr) {   // a gated launch is expected to find nothing to do
-        int any = 0;
-        for (int ql = r0 + (int)threadIdx.x; ql < r1; ql += blockDim.x) any |= o.gate[ql] > o.gate_cap;
-        if (!__syncthreads_or(any)) return;
-    }
-    // ---- the tile's slabs -> shared memory (one bulk copy per (head row, sub-tile) that has one)
-    const uint32_t cbar_a = sc_smem_u32(&cbar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cbar_a) : "memory");
+    const uint32_t zbar_a = sc_smem_u32(&zbar[w]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(zbar_a) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < B2R_HEAD_TERMS) okm[threadIdx.x] = 0;
-    __syncthreads();
-    if (warp == 0 && slabs) {
-        uint32_t bytes = 0;
-        for (int i = lane; i < B2R_HEAD_TERMS * B2R_SUBTILES; i += 32) {
-            const int h = i / B2R_SUBTILES, sseg = i % B2R_SUBTILES;
-            const int32_t sid = slab_idx[(size_t)h * n_seg + (size_t)tile * B2R_SUBTILES + sseg];
-            if (sid >= 0 && sid < n_slabs) {
-                atomicOr(&okm[h], 1 << sseg);
-                const uint32_t nb = (uint32_t)(T2K_SUB * sizeof(val_t));
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                        sc_smem_u32(cache + (size_t)h * T2K_TILE + (size_t)sseg * T2K_SUB)),
-                    "l"(static_cast<const val_t *>(slab_val) + (size_t)sid * T2K_SUB), "r"(nb), "r"(cbar_a)
-                    : "memory");
-                bytes += nb;
-            }
+    __syncwarp();
+    uint32_t zphase = 0;
+    const int qs = q_ptr[q], qe = q_ptr[q + 1];
+    auto tile_of = [&](int y) -> int {
+        return tile_mode == SC_TILES_ALL ? y : y * tile_step;
+    };
+    // A CTA walks several doc tiles (stride gridDim.y).  A query of <= 32 terms is staged ONCE, lane j keeping
+    // term j's weights and the base of its offset row; per tile only the two offsets of the warp's posting range
+    // are fetched, one tile ahead, so the dependent chain q_terms -> dense_id -> offsets -> postings is paid once
+    // per CTA instead of once per tile.
+    const bool staged = qe - qs <= 32;
+    const uint32_t *my_row = nullptr;  // dense: offsets per sub-tile; sparse: offsets per tile
+    const int32_t *my_slab_row = nullptr;  // dense term with usable slabs: slab numbers per sub-tile
+    typename TermW<KIND>::type my_idf = 0, my_qw = 0;
+    int my_dense = 0;
+    uint32_t nxt_beg = 0, nxt_end = 0;
+    int32_t nxt_slab = -1;
+    if (staged && lane < qe - qs) {
+        const int t = q_terms[qs + lane];
+        my_qw = q_weights[qs + lane];
+        my_idf = idf[t];
+        const int32_t did = dense_id[t];
+        my_dense = did >= 0;
+        my_row = my_dense ? dense_ptr + (size_t)did * dense_row + w : blk_ptr + (size_t)t * n_tiles;
+        // slabs add (idf * 0) * q for absent documents: only exact when both weights are finite
+        if (slab_idx != nullptr && my_dense && isfinite((float)my_idf) && isfinite((float)my_qw))
+            my_slab_row = slab_idx + (size_t)did * n_seg + w;
+        if ((int)blockIdx.y < n_y) {
+            const size_t i0 = (size_t)tile_of(blockIdx.y) * (my_dense ? B2R_SUBTILES : 1);
+            nxt_beg = my_row[i0];
+            nxt_end = my_row[i0 + 1];
+            if (my_slab_row != nullptr) nxt_slab = my_slab_row[i0];
         }
-#pragma unroll
-        for (int ofs = 16; ofs; ofs >>= 1) bytes += __shfl_xor_sync(full, bytes, ofs);
-        // (a copy that completes before this arrive only drives the transaction count negative for a moment:
-        // the phase cannot complete before the one pending arrival below)
-        if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cbar_a), "r"(bytes) : "memory");
-    } else if (threadIdx.x == 0 && !slabs) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cbar_a) : "memory");
     }
-    __syncthreads();   // okm is complete
+  for (int y = blockIdx.y; y < n_y; y += gridDim.y) {
+    // The sub-tile needs no clearing when the first term that touches it is a slab (it writes every accumulator).
+    bool need_clear = true;
+    if (staged) {
+        const unsigned nonempty = __ballot_sync(full, nxt_beg != nxt_end);
+        const unsigned slabm = __ballot_sync(full, nxt_slab >= 0);
+        need_clear = nonempty == 0 || !((slabm >> (__ffs(nonempty) - 1)) & 1u);
+    }
+    if (need_clear && lane == 0) {  // clear my sub-tile's accumulators with one bulk copy; overlaps the term staging below
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar_a), "r"((uint32_t)(sub * 8))
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                sc_smem_u32(acc_w)),
+            "l"(g_zero_page), "r"((uint32_t)(sub * 8)), "r"(zbar_a)
+            : "memory");
+    }
+    const int tile = tile_of(y);
+    const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
+    const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
+    uint32_t my_beg = nxt_beg, my_end = nxt_end;
+    int32_t my_slab = nxt_slab;
+    if (staged && my_row != nullptr && y + (int)gridDim.y < n_y) {  // offsets of the next tile: used one iteration later
+        const size_t i1 = (size_t)tile_of(y + gridDim.y) * (my_dense ? B2R_SUBTILES : 1);
+        nxt_beg = my_row[i1];
+        nxt_end = my_row[i1 + 1];
+        if (my_slab_row != nullptr) nxt_slab = my_slab_row[i1];
+    }
 
-    const uint32_t my_doc0 = (uint32_t)tile * T2K_TILE + (uint32_t)w * T2K_SUB;
-    bool cache_ready = false;
-    for (int cur = r0; cur < r1;) {
-        // ---- chunk of queries [cur, cur + c): as many as fit the record and query capacities (at least one)
-        const int cnt = min(r1 - cur, T2K_Q_CAP);
-        const int tb = q_ptr[q0 + cur];
-        int fits = 0;
-        if ((int)threadIdx.x < cnt) fits = q_ptr[q0 + cur + threadIdx.x + 1] - tb <= T2K_REC_CAP;
-        int c = __syncthreads_count(fits);   // (q_ptr is monotone: the queries that fit form a prefix)
-        if (c < 1) c = 1;
-        const int n_staged = min(q_ptr[q0 + cur + c] - tb, T2K_REC_CAP);
-        for (int i = threadIdx.x; i < n_staged; i += blockDim.x)
-            rec[i] = t2k_make_record(tb + i, tile, n_tiles, q_terms, q_weights, idf, dense_id, dense_ptr, blk_ptr, post_doc,
-                                     okm, slabs, cum + (size_t)i * T2K_CUM);
-        for (int i = threadIdx.x; i <= c; i += blockDim.x) qoff[i] = q_ptr[q0 + cur + i] - tb;
-        if (OUT == SC_OUT_FUSED) {
-            for (int i = threadIdx.x; i < c; i += blockDim.x) {
-                const uint64_t thr = o.thr_keys[cur + i];
-                const uint32_t thr_hi = (uint32_t)(thr >> 32);
-                // A document can only beat thr if f32(acc) >= the threshold score.  The accumulators are compared in
-                // f64 against the f32 value just below the threshold score: acc < pred(thr_f) implies f32(acc) <=
-                // pred(thr_f) < thr_f (rounding is monotone); only survivors are converted and keyed.  Ordered
-                // encoding: -1 = next smaller f32; 0x7fffffff would be -0.0 (== +0.0 in the ranking): skip it; at or
-                // below -inf (0x007fffff) there is nothing smaller: no filter (thr_hi == 0: no threshold at all)
-                uint32_t thr_ord = thr_hi > 0x007fffffu ? thr_hi - 1u : 0u;
-                if (thr_ord == 0x7fffffffu) thr_ord = 0x7ffffffeu;
-                double lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
-                // "strictly positive scores only" (kth_of_maxima's positive floor): nothing below 2^-150 rounds to a
-                // positive f32, so the untouched documents (acc == 0) never reach the conversion path
-                if (thr == ((0x80000000ull << 32) | 0xFFFFFFFFull)) lo = __longlong_as_double(0x3690000000000000ll);
-                qthr[i].thr = thr;
-                qthr[i].lo = lo;
-            }
-        }
-        __syncthreads();
-        if (!cache_ready) {
-            sc_mbar_wait(cbar_a, 0);   // the slab bytes are visible
-            cache_ready = true;
-        }
+    bool cleared = !need_clear;
+    bool first = true;  // no term has touched this warp's sub-tile yet (warp-uniform)
 
-        for (int qi = slot; qi < c; qi += T2K_SLOTS) {
-            const int ql = cur + qi;
-            if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap) continue;
-            const int i0 = qoff[qi], i1 = qoff[qi + 1];
-            // where the sub-tile's accumulators are (warp-uniform): 0 nowhere yet (all +0.0), 1 registers, 2 shared memory
-            int st = 0;
-            double2 r[T2K_PAIRS];
-#pragma unroll
-            for (int cc = 0; cc < T2K_PAIRS; ++cc) r[cc] = make_double2(0.0, 0.0);
-            auto to_smem = [&]() {
-                if (st == 2) return;
-#pragma unroll
-                for (int cc = 0; cc < T2K_PAIRS; ++cc) *reinterpret_cast<double2 *>(acc_w + 64 * cc + 2 * lane) = r[cc];
-                st = 2;     // (r[] holds zeros in state 0)
-                __syncwarp();
-            };
-            for (int i = i0; i < i1; ++i) {
-                T2KRec rc;
-                uint16_t cum_l[T2K_CUM];
-                const bool staged = i < n_staged;
-                if (staged) rc = rec[i];
-                else rc = t2k_make_record(tb + i, tile, n_tiles, q_terms, q_weights, idf, dense_id, dense_ptr, blk_ptr, post_doc,
-                                          okm, slabs, cum_l);     // (a query longer than the record capacity)
-                const uint32_t kind = rc.kind & 0xFFu;
-                if (kind >= 2u && ((rc.kind >> (8 + w)) & 1u)) {
-                    // ---- slab: register accumulators
-                    if (st == 2) {
-#pragma unroll
-                        for (int cc = 0; cc < T2K_PAIRS; ++cc)
-                            r[cc] = *reinterpret_cast<const double2 *>(acc_w + 64 * cc + 2 * lane);
-                    }
-                    st = 1;
-                    const val2_t *cv = reinterpret_cast<const val2_t *>(cache + (size_t)(kind - 2u) * T2K_TILE +
-                                                                        (size_t)w * T2K_SUB) + lane;
-                    if (KIND == B2R_KIND_BM25) {
-                        const double wi = (double)rc.idf, wq = (double)rc.w;
-#pragma unroll
-                        for (int cc = 0; cc < T2K_PAIRS; ++cc) {
-                            const val2_t u = cv[32 * cc];
-                            r[cc].x = __dadd_rn(r[cc].x, __dmul_rn(__dmul_rn(wi, (double)u.x), wq));
-                            r[cc].y = __dadd_rn(r[cc].y, __dmul_rn(__dmul_rn(wi, (double)u.y), wq));
-                        }
-                    } else {
-#pragma unroll
-                        for (int cc = 0; cc < T2K_PAIRS; ++cc) {
-                            const val2_t u = cv[32 * cc];
-                            // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens
-                            r[cc].x = __dadd_rn(r[cc].x, (double)__fmul_rn(__fmul_rn((float)u.x, rc.w), rc.idf));
-                            r[cc].y = __dadd_rn(r[cc].y, (double)__fmul_rn(__fmul_rn((float)u.y, rc.w), rc.idf));
-                        }
-                    }
-                } else if (kind >= 1u) {
-                    // ---- dense term (or a head term whose segment has no slab here): my bank-scheduled segment
-                    uint32_t cb, ce;
-                    if (staged) {
-                        cb = cum[(size_t)i * T2K_CUM + w];
-                        ce = cum[(size_t)i * T2K_CUM + w + 1];
-                    } else {
-                        cb = cum_l[w];
-                        ce = cum_l[w + 1];
-                    }
-                    if (cb == ce) continue;
-                    to_smem();
-                    apply_dense_term<KIND, false>(rc.base + cb, rc.base + ce, lane, my_doc0, post_doc, post_val, acc_w, rc.idf, rc.w);
-                    __syncwarp();
+    for (int j0 = qs; j0 < qe; j0 += 32) {
+        const int nt = min(32, qe - j0);
+        if (!staged) {  // long query: lane j stages term j0+j for this tile (dense: my sub-tile; sparse: the tile block)
+            my_beg = my_end = 0;
+            my_dense = 0;
+            my_slab = -1;
+            if (lane < nt) {
+                const int t = q_terms[j0 + lane];
+                my_qw = q_weights[j0 + lane];
+                my_idf = idf[t];
+                const int32_t did = dense_id[t];
+                if (did >= 0) {
+                    const uint32_t *row = dense_ptr + (size_t)did * dense_row + my_sub;
+                    my_beg = row[0];
+                    my_end = row[1];
+                    my_dense = 1;
+                    if (slab_idx != nullptr && isfinite((float)my_idf) && isfinite((float)my_qw))
+                        my_slab = slab_idx[(size_t)did * n_seg + my_sub];
                 } else {
-                    // ---- sparse term: the tile's block, shared by all warps (kept in L1); the mask says whether it has
-                    // a posting in my sub-tile (blocks of more than 16 postings are always scanned)
-                    if (!((rc.kind >> (8 + w)) & 1u)) continue;
-                    const uint32_t n = rc.kind >> 16;
-                    to_smem();
-                    const double w_idf64 = (double)rc.idf, w_q64 = (double)rc.w;
-                    for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-                        const uint32_t p = p0 + lane;
-                        if (p < n) {
-                            const uint32_t rel = __ldg(post_doc + rc.base + p) - my_doc0;
-                            if (rel < (uint32_t)T2K_SUB) {
-                                const double u = load_val<KIND>(post_val, rc.base + p);
-                                apply_posting<KIND, false>(acc_w, rel, u, rc.idf, rc.w, w_idf64, w_q64);
-                            }
-                        }
-                    }
-                    __syncwarp();
+                    const size_t e = (size_t)t * n_tiles + tile;
+                    my_beg = blk_ptr[e];
+                    my_end = blk_ptr[e + 1];
                 }
             }
-
-            // ---- epilogue over the sub-tile's accumulators: pair (i, i + 1), i = 64 cc + 2 lane
-            if (st == 2) {
-#pragma unroll
-                for (int cc = 0; cc < T2K_PAIRS; ++cc) r[cc] = *reinterpret_cast<const double2 *>(acc_w + 64 * cc + 2 * lane);
-            }
-            if (OUT == SC_OUT_DENSE) {
-                float *out_row = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * T2K_TILE + w * T2K_SUB + 2 * lane;
-#pragma unroll
-                for (int cc = 0; cc < T2K_PAIRS; ++cc)
-                    *reinterpret_cast<float2 *>(out_row + 64 * cc) =
-                        make_float2(__double2float_rn(r[cc].x), __double2float_rn(r[cc].y));
-            } else if (OUT == SC_OUT_MAXIMA) {
-                // one maximum per lane over the (valid) documents it owns; f32(max) == max(f32): rounding is monotone
-                double m = -__longlong_as_double(0x7ff0000000000000ll);
-#pragma unroll
-                for (int cc = 0; cc < T2K_PAIRS; ++cc) {
-                    const uint32_t doc = my_doc0 + 64 * cc + 2 * lane;
-                    if (doc < o.n_docs) m = fmax(m, r[cc].x);
-                    if (doc + 1 < o.n_docs) m = fmax(m, r[cc].y);
-                }
-                o.scores[(int64_t)ql * o.scores_stride + (int64_t)y * SC_GROUPS_PER_TILE + w * 32 + lane] = __double2float_rn(m);
+        }
+        if (!cleared) {  // the staging loads above were issued before this wait
+            sc_mbar_wait(zbar_a, zphase);
+            cleared = true;
+        }
+        for (int j = 0; j < nt; ++j) {
+            const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
+            if (beg == end) continue;  // warp-uniform
+            const int dense = __shfl_sync(full, my_dense, j);
+            const typename TermW<KIND>::type w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
+            const int32_t slab = __shfl_sync(full, my_slab, j);
+            if (slab >= 0) {
+                if (first) apply_slab<KIND, true>(acc_w, slab_val, slab, sub, lane, (float)w_idf, (float)w_q);
+                else apply_slab<KIND, false>(acc_w, slab_val, slab, sub, lane, (float)w_idf, (float)w_q);
             } else {
-                const T2KThr th = qthr[qi];
-                bool any = false;
+                if (first) apply_term<KIND, true>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
+                else apply_term<KIND, false>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
+            }
+            first = false;
+            __syncwarp();
+        }
+    }
+
+    if (!cleared) sc_mbar_wait(zbar_a, zphase);  // query without terms
+    if (need_clear) zphase ^= 1;
+    if (OUT == SC_OUT_DENSE) {
+        float *out = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * tile_docs + w * sub;
+        for (int i = lane * 2; i < sub; i += 64) {
+            double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            *reinterpret_cast<float2 *>(out + i) = make_float2(__double2float_rn(a.x), __double2float_rn(a.y));
+        }
+    } else if (OUT == SC_OUT_MAXIMA) {
+        // one maximum per lane over the (valid) documents it reads; f32(max) == max(f32): rounding is monotone
+        double m = -__longlong_as_double(0x7ff0000000000000ll);
+        for (int i = lane * 2; i < sub; i += 64) {
+            const double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            const uint32_t doc = my_doc0 + i;
+            if (doc < o.n_docs) m = fmax(m, a.x);
+            if (doc + 1 < o.n_docs) m = fmax(m, a.y);
+        }
+        o.scores[(int64_t)ql * o.scores_stride + (int64_t)y * SC_GROUPS_PER_TILE + w * 32 + lane] = __double2float_rn(m);
+    } else {
+        const uint64_t thr = o.thr_keys[ql];
+        const uint32_t thr_hi = (uint32_t)(thr >> 32);
+        // A document can only beat thr if f32(acc) >= the threshold score.  Instead of converting all 4096
+        // accumulators of the tile, they are compared in f64 against the f32 value just below the threshold
+        // score: acc < pred(thr_f) implies f32(acc) <= pred(thr_f) < thr_f (rounding is monotone).  Only
+        // survivors are converted and keyed (measured: -2 % kernel time).  thr_hi == 0: no threshold yet.
+        // ordered encoding: -1 = next smaller f32; 0x7fffffff would be -0.0 (== +0.0 in the ranking): skip it;
+        // at or below -inf (0x007fffff) there is nothing smaller: no filter
+        uint32_t thr_ord = thr_hi > 0x007fffffu ? thr_hi - 1u : 0u;
+        if (thr_ord == 0x7fffffffu) thr_ord = 0x7ffffffeu;
+        double thr_lo = thr_ord ? (double)unord_f32(thr_ord) : -__longlong_as_double(0x7ff0000000000000ll);
+        // "strictly positive scores only" (kth_of_maxima's positive floor): nothing below 2^-150 rounds to a
+        // positive f32, so the untouched documents (acc == 0) never reach the conversion path
+        if (thr == ((0x80000000ull << 32) | 0xFFFFFFFFull)) thr_lo = __longlong_as_double(0x3690000000000000ll);
+        // (measured: testing 8 documents per step through an fmax tree is slower than this plain pair loop)
+        for (int i = lane * 2; i < sub; i += 64) {
+            const double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+            if (a.x >= thr_lo || a.y >= thr_lo) {
+                const double av[2] = {a.x, a.y};
 #pragma unroll
-                for (int cc = 0; cc < T2K_PAIRS; ++cc) any |= (r[cc].x >= th.lo) | (r[cc].y >= th.lo);
-                if (any) {
-#pragma unroll
-                    for (int cc = 0; cc < T2K_PAIRS; ++cc) {
-                        const double av[2] = {r[cc].x, r[cc].y};
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const uint32_t doc = my_doc0 + 64 * cc + 2 * lane + e;
-                            if (av[e] >= th.lo && doc < o.n_docs) {
-                                const uint64_t key = make_key(ord_f32(__double2float_rn(av[e])), o.doc_id_base + doc);
-                                if (key > th.thr) {
-                                    const int slot_c = atomicAdd(o.cand_cnt + ql, 1);
-                                    if (slot_c < o.cap) o.cand[(int64_t)ql * o.cap + slot_c] = key;
-                                }
-                            }
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t doc = my_doc0 + i + c;
+                    if (av[c] >= thr_lo && doc < o.n_docs) {
+                        const uint64_t key = make_key(ord_f32(__double2float_rn(av[c])), o.doc_id_base + doc);
+                        if (key > thr) {
+                            const int slot = atomicAdd(o.cand_cnt + ql, 1);
+                            if (slot < o.cap) o.cand[(int64_t)ql * o.cap + slot] = key;
                         }
                     }
                 }
             }
-            __syncwarp();   // the next query's writes must not overtake this epilogue's reads
-        }  // queries of the chunk
-        __syncthreads();   // the records are about to be replaced
-        cur += c;
+        }
     }
+    // the next tile's bulk clear (async proxy) must not overtake this tile's accumulator reads (generic proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+  }  // tile loop
 }
-
-constexpr size_t SC_SMEM_MAX = 226 * 1024;   // dynamic shared memory of a scorer CTA (227 KB minus the static part)
 
 struct ScoreLaunch {
     const b2r_index *ix;
@@ -813,95 +425,44 @@ struct ScoreLaunch {
     cudaStream_t st;
 };
 
-static bool g_slabs_enabled = true;   // b2r_set_slabs: test / profiling hook (same results either way)
-
-// CTAs per doc tile (= query ranges): enough CTAs for several waves over the 148 SMs, but every CTA should walk
-// enough queries to pay for its slab copy (B2R_SCORE_RANGES overrides: tuning experiments only)
-static int ranges_override() {
-    const char *e = getenv("B2R_SCORE_RANGES");
+// doc tiles walked by one CTA of the scorer (B2R_SCORE_TILES_PER_CTA overrides it: tuning experiments only)
+static int tiles_per_cta_default() {
+    const char *e = getenv("B2R_SCORE_TILES_PER_CTA");
     const int v = e ? atoi(e) : 0;
-    return v >= 1 && v <= 65535 ? v : 0;
+    return v >= 1 && v <= 64 ? v : 4;
 }
-static const int g_ranges_override = ranges_override();
-static const int g_generic_scorer = [] {   // B2R_GENERIC_SCORER=1: tile 2048 through the generic kernel (A/B only)
-    const char *e = getenv("B2R_GENERIC_SCORER");
-    return e ? atoi(e) : 0;
-}();
-static const int g_score_diag = [] {
-    const char *e = getenv("B2R_SCORE_DIAG");
-    return e ? atoi(e) : 0;
-}();
-
-template <int KIND, int OUT, bool SLABS>
-static int launch_score_impl(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
-    const b2r_index *ix = L.ix;
-    const size_t acc_bytes = (size_t)ix->tile_docs * sizeof(double);
-    const size_t cache_bytes = SLABS ? (size_t)B2R_HEAD_TERMS * ix->tile_docs * (KIND == B2R_KIND_BM25 ? 8 : 4) : 0;
-    const size_t rec_bytes = (size_t)SC_REC_CAP * sizeof(int4);
-    int slots = (int)((SC_SMEM_MAX - rec_bytes - cache_bytes) / acc_bytes);
-    slots = slots > SC_MAX_SLOTS ? SC_MAX_SLOTS : (slots < 1 ? 1 : slots);
-    if (slots > nq) slots = nq;
-    const size_t smem = (size_t)slots * acc_bytes + cache_bytes + rec_bytes;
-    int ranges = g_ranges_override ? g_ranges_override : (148 * 8 + n_y - 1) / n_y;
-    const int max_ranges = (nq + 4 * slots - 1) / (4 * slots);   // >= 4 queries per slot and CTA
-    if (ranges > max_ranges) ranges = max_ranges;
-    if (ranges < 1) ranges = 1;
-    const int range_len = (nq + ranges - 1) / ranges;
-    ranges = (nq + range_len - 1) / range_len;
-    auto kern = score_tiles_kernel<KIND, OUT, SLABS>;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM_MAX));
-        attr_set = true;
-    }
-    dim3 grid((unsigned)ranges, (unsigned)n_y);
-    kern<<<grid, slots * SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
-                                                   ix->slab_idx, ix->slab_val, ix->n_slabs, ix->n_tiles, ix->tile_docs,
-                                                   L.q_ptr, L.q_terms, L.q_weights, L.idf, q0, nq, range_len, tile_mode,
-                                                   tile_step, OUT == SC_OUT_FUSED ? g_score_diag : 0, o);
-    B2R_LAUNCH_CHECK();
-    return B2R_OK;
-}
-
-template <int KIND, int OUT>
-static int launch_score_t2k(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
-    const b2r_index *ix = L.ix;
-    // CTAs per doc tile (= query ranges): several waves over the 148 SMs, but at least ~32 queries per CTA so that the
-    // slab copy and the record staging are paid for
-    int ranges = g_ranges_override ? g_ranges_override : (148 * 8 + n_y - 1) / n_y;
-    const int max_ranges = (nq + 31) / 32;
-    if (ranges > max_ranges) ranges = max_ranges;
-    if (ranges < 1) ranges = 1;
-    const int range_len = (nq + ranges - 1) / ranges;
-    ranges = (nq + range_len - 1) / range_len;
-    auto kern = score_t2k_kernel<KIND, OUT>;
-    constexpr size_t smem = t2k_smem_bytes<KIND>();
-    static_assert(smem <= SC_SMEM_MAX, "t2k shared memory");
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const bool slabs = g_slabs_enabled && ix->slab_idx && ix->slab_val && ix->n_slabs > 0;
-    dim3 grid((unsigned)ranges, (unsigned)n_y);
-    kern<<<grid, T2K_SLOTS * SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
-                                                       slabs ? ix->slab_idx : nullptr, ix->slab_val, slabs ? ix->n_slabs : 0,
-                                                       ix->n_tiles, L.q_ptr, L.q_terms, L.q_weights, L.idf, q0, nq, range_len,
-                                                       tile_mode, tile_step, o);
-    B2R_LAUNCH_CHECK();
-    return B2R_OK;
-}
+static const int g_tiles_per_cta = tiles_per_cta_default();
+static bool g_slabs_enabled = true;   // b2r_set_slabs: test / profiling hook (same results either way)
 
 template <int OUT>
 static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
     if (nq == 0 || n_y == 0) return B2R_OK;
     const b2r_index *ix = L.ix;
-    if (ix->tile_docs == T2K_TILE && !g_generic_scorer) {
-        if (ix->kind == B2R_KIND_BM25) return launch_score_t2k<B2R_KIND_BM25, OUT>(L, q0, nq, tile_mode, tile_step, n_y, o);
-        return launch_score_t2k<B2R_KIND_IMPACT, OUT>(L, q0, nq, tile_mode, tile_step, n_y, o);
+    const size_t smem = (size_t)ix->tile_docs * sizeof(double);
+    // a gated launch is expected to do nothing: keep its grid tiny (each CTA walks n_y / 4 tiles if it runs)
+    // tiles per CTA: enough CTAs must remain to fill the GPU a few times over (148 SMs x 6 CTAs)
+    int per_cta = g_tiles_per_cta;
+    while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 6 * 4) per_cta >>= 1;
+    const int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
+    dim3 grid((unsigned)nq, (unsigned)grid_y);
+    // slabs: sub-tiles of >= 256 documents (the slab loop moves 4 x 64 documents per step)
+    const int32_t *slabs = (g_slabs_enabled && ix->slab_idx && ix->slab_val && ix->n_slabs > 0 && ix->tile_docs >= 2048)
+                               ? ix->slab_idx : nullptr;
+    if (ix->kind == B2R_KIND_BM25) {
+        auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;
+        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
+                                               slabs, ix->slab_val, ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms,
+                                               L.q_weights, L.idf, q0, tile_mode, tile_step, n_y, o);
+    } else {
+        auto kern = score_tiles_kernel<B2R_KIND_IMPACT, OUT>;
+        B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
+                                               slabs, ix->slab_val, ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms,
+                                               L.q_weights, L.idf, q0, tile_mode, tile_step, n_y, o);
     }
-    if (ix->kind == B2R_KIND_BM25) return launch_score_impl<B2R_KIND_BM25, OUT, false>(L, q0, nq, tile_mode, tile_step, n_y, o);
-    return launch_score_impl<B2R_KIND_IMPACT, OUT, false>(L, q0, nq, tile_mode, tile_step, n_y, o);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
 }
 
 static int check_index(const b2r_index *ix) {
@@ -968,7 +529,7 @@ using namespace b2r;
 
 // test / profiling hook: 0 disables the fused-selection path (plain score + select is used)
 extern "C" void b2r_set_fused_selection(int enabled) { b2r::g_fused_enabled = enabled != 0; }
-// test / profiling hook: 0 makes the scorer ignore an index's slabs (shared-memory accumulators only)
+// test / profiling hook: 0 makes the scorer ignore an index's slabs (posting lists only)
 extern "C" void b2r_set_slabs(int enabled) { b2r::g_slabs_enabled = enabled != 0; }
 
 extern "C" int b2r_set_profiling(int enabled) {

@@ -765,15 +765,14 @@ def test_full_size_1m_docs_properties(b2r):
 
 # ----------------------------------------------------------------------------------- slabs (register accumulators)
 @pytest.mark.parametrize("kind", ["bm25", "impact"])
-def test_slab_path_equals_shared_memory_path_and_oracle(b2r, kind):
-    """The 8 dense terms with the largest df own dense rows 0..7 (head rows); their segments covering >= 1/4 of a
-    sub-tile exist as slabs, which the scorer keeps in shared memory per doc tile and applies to register accumulators.
-    Checked: (1) head rows are the top-df terms and the slabs hold exactly the postings of their segment, 0 elsewhere;
-    (2) dense scores, fused and plain top-k are bit-identical with slabs on and off and equal the oracle.  The
-    vocabulary is partly REVERSED for half of the runs, so that head terms carry large ids: sparse terms then come
-    first and the slab path has to pick the accumulators up from shared memory (and spill back when a sparse term
-    follows)."""
-    tile_docs = 2048
+@pytest.mark.parametrize("tile_docs", [2048, 4096])
+def test_slab_path_equals_posting_path_and_oracle(b2r, kind, tile_docs):
+    """Dense-term segments covering >= 1/4 of a sub-tile also exist as slabs (values in document order, 0 = no
+    posting), which the scorer streams instead of the posting list.  Checked: (1) the 8 dense terms with the largest df
+    own dense rows 0..7 and the slabs hold exactly the postings of their segment, 0 elsewhere; (2) dense scores, fused
+    and plain top-k are bit-identical with slabs on and off and equal the oracle.  The vocabulary is partly REVERSED
+    for half of the runs, so that head terms carry large ids: sparse terms then come first, the sub-tile is cleared
+    and the slab path does read-modify-write instead of its first-term store."""
     from b200ret import synthetic as S
     n_docs, n_vocab, k = 70_000 + 13, 6000, 10
     data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 60, seed=51)
