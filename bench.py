@@ -245,14 +245,12 @@ def run_b200(args):
     w = make_workload(args.workload, args.n_queries)
     n_docs, k = w["n_docs"], w["k"]
     b200ret.set_bank_schedule(bool(args.bank_schedule))
-    b200ret.set_slabs(bool(args.slabs))
     lo, hi = shard_range(n_docs, world, rank)
     s, e = w["indptr"][lo], w["indptr"][hi]
     ix = b200ret.TermMajorIndex.from_csr(w["data"][s:e], w["indices"][s:e], w["indptr"][lo:hi + 1] - s, w["dl"][lo:hi],
                                          n_vocab=w["n_vocab"], idf=w["idf"], avgdl=w["avgdl"], doc_id_base=lo,
                                          tile_docs=args.tile_docs)
     sharded = ShardedBM25(ix)
-    n_slabs = ix.n_slabs if args.slabs else 0
     nq = len(w["q_ptr"]) - 1
     d_ptr = torch.from_numpy(w["q_ptr"]).to(dev)
     d_terms = torch.from_numpy(w["q_terms"]).to(dev)
@@ -437,7 +435,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
-            "run": {"sharding": f"doc-sharded x{world}", "tile_docs": args.tile_docs, "slabs_rank0": n_slabs,
+            "run": {"sharding": f"doc-sharded x{world}", "tile_docs": args.tile_docs,
                     "postings_touched_per_step_rank0": postings, "cuda_graph_replay": graphed,
                     "launches_per_step": launches_per_step,
                     "selection": ("fused: threshold = k-th largest group maximum of every %dth tile, all tiles scored with "
@@ -642,10 +640,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--tile-docs", type=int, default=2048)
+    ap.add_argument("--tile-docs", type=int, default=4096)
     ap.add_argument("--check", type=int, default=None,
                     help="queries checked against the oracle (default: all of them at N = 1, 64 at N > 1)")
-    ap.add_argument("--slabs", type=int, default=1, help="0 = scorer ignores the index's slabs (A/B measurement only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", type=int, default=1, help="0 = skip the C1 / C3 / C5 secondary measurements")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the timed step as a CUDA graph (0 = eager)")

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define B2R_VERSION 101
+#define B2R_VERSION 100
 #define B2R_TOPK_MAX_FAST 1024 /* larger k takes the full-sort path of b2r_topk */
 
 typedef enum b2r_status {
@@ -84,22 +84,8 @@ typedef struct b2r_index {
     int32_t *dense_id;   /* [n_vocab] row of dense_ptr, or -1 */
     uint32_t *dense_ptr; /* [n_dense_max * (n_tiles * B2R_SUBTILES + 1)] */
     int32_t n_dense_max; /* rows allocated in dense_ptr (from b2r_index_sizes_for) */
-    int32_t n_slabs;     /* slabs in slab_val (0 = none; from b2r_index_slab_count) */
-    /* Slabs.  A (dense term, sub-tile) segment that holds postings for >= B2R_SLAB_MIN_NUM/B2R_SLAB_MIN_DEN of the
-     * sub-tile's documents ADDITIONALLY exists as a SLAB: the sub-tile's tile_docs/B2R_SUBTILES posting values in
-     * document order, 0 where a document has no posting.  The scorer streams a slab with coalesced 16-byte loads and
-     * updates the accumulators 16 bytes at a time: no document ids, no bank conflicts, a fifth of the instructions of
-     * the posting loop; adding (idf * 0) * qtf for an absent document leaves the f64 accumulator bit-identical.
-     * slab_idx[r * n_tiles * B2R_SUBTILES + S] is the slab number of dense row r in sub-tile S, or -1.  Slabs exist
-     * for tile_docs >= B2R_SLAB_TILE_DOCS; slab_idx == NULL or n_slabs == 0 turns them off.  (The B2R_HEAD_TERMS
-     * dense terms with the largest document frequency own dense rows 0 .. B2R_HEAD_TERMS-1.) */
-    int32_t *slab_idx;   /* [n_dense_max * n_tiles * B2R_SUBTILES] */
-    void *slab_val;      /* [n_slabs * tile_docs / B2R_SUBTILES] f64 (BM25) or f32 (IMPACT) */
+    int32_t reserved0;
 } b2r_index;
-#define B2R_HEAD_TERMS 8
-#define B2R_SLAB_TILE_DOCS 2048
-#define B2R_SLAB_MIN_NUM 1
-#define B2R_SLAB_MIN_DEN 4
 
 typedef struct b2r_index_sizes {
     size_t post_doc_bytes;
@@ -109,7 +95,6 @@ typedef struct b2r_index_sizes {
     size_t dense_id_bytes;
     size_t dense_ptr_bytes;
     int64_t n_dense_max;
-    size_t slab_idx_bytes;
 } b2r_index_sizes;
 
 int b2r_version(void);
@@ -131,24 +116,17 @@ int b2r_index_build(const b2r_index *ix, const float *tf, const int32_t *indices
                     size_t scratch_bytes, void *stream);
 /* Synchronises the stream and reports malformed input (term id out of range) found by the build. */
 int b2r_index_build_status(const void *scratch, void *stream);
-/* Slabs (see b2r_index).  b2r_index_build marks the slab segments in ix->slab_idx (when it is non-NULL; slabs exist
- * for tile_docs >= B2R_SLAB_TILE_DOCS) and counts them; b2r_index_slab_count synchronises and returns the count, the caller
- * allocates b2r_index_slab_bytes(...) for ix->slab_val, sets ix->n_slabs and calls b2r_index_build_slabs, which
- * fills the slabs from post_doc / post_val.  An index whose slab step is skipped is complete and searchable. */
-int b2r_index_slab_count(const void *scratch, void *stream, int32_t *n_slabs);
-size_t b2r_index_slab_bytes(int32_t n_slabs, int32_t tile_docs, int32_t kind);
-int b2r_index_build_slabs(const b2r_index *ix, void *stream);
 
 /* ---- On-disk form of a b2r_index (the reference only caches the doc-major CSR as
- * an .npz, evaluate_rag_pipeline.py:280-312).  One file = this header (4096 bytes) followed by the eight device
+ * an .npz, evaluate_rag_pipeline.py:280-312).  One file = this header (4096 bytes) followed by the six device
  * buffers verbatim, each starting on a 4096-byte boundary, so a shard can be read (or cuFile-DMAed) straight
  * into HBM with no re-layout.  Little-endian.  The buffers hold shard-local document indices: doc_id_base may
  * be changed at load time. */
 #define B2R_FILE_MAGIC "B2RIDX01"
-#define B2R_FILE_VERSION 2u
+#define B2R_FILE_VERSION 1u
 #define B2R_FILE_ALIGN 4096u
 enum { B2R_SEC_POST_DOC = 0, B2R_SEC_POST_VAL, B2R_SEC_BLK_PTR, B2R_SEC_DENSE_ID, B2R_SEC_DENSE_PTR, B2R_SEC_IDF,
-       B2R_SEC_SLAB_IDX, B2R_SEC_SLAB_VAL, B2R_SEC_COUNT };
+       B2R_SEC_COUNT };
 typedef struct b2r_file_section {
     uint64_t offset;   /* from the start of the file, multiple of B2R_FILE_ALIGN */
     uint64_t bytes;    /* the device buffer size (b2r_index_sizes_for); idf: 4 * n_vocab */
@@ -160,13 +138,12 @@ typedef struct b2r_index_file_header {
     uint32_t header_bytes; /* B2R_FILE_ALIGN */
     int64_t n_docs, doc_id_base, nnz;
     int32_t n_vocab, tile_docs, n_tiles, kind, n_dense_max, subtiles /* B2R_SUBTILES */;
-    int32_t n_slabs, reserved1;
     double k1, b, avgdl;   /* baked into post_val of a BM25 index */
     b2r_file_section sections[B2R_SEC_COUNT];
 } b2r_index_file_header;
 /* Host-only helpers (no device access).  b2r_checksum64: order-dependent 64-bit checksum of a byte range
  * (any length).  b2r_index_file_layout: fills magic/version/sizes/offsets of *hdr from its dimension fields
- * (n_docs, nnz, n_vocab, tile_docs, kind, n_dense_max, n_slabs; checksums are left 0) and returns the total file size in
+ * (n_docs, nnz, n_vocab, tile_docs, kind, n_dense_max; checksums are left 0) and returns the total file size in
  * *file_bytes.  b2r_index_file_check: validates a header read from a file of file_bytes bytes (magic, version,
  * dimensions, section sizes and bounds) -- B2R_ERR_DATA with a message when it is not a loadable index. */
 uint64_t b2r_checksum64(const void *data, size_t bytes);
@@ -194,8 +171,6 @@ int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q
 /* Test / profiling hook: 0 makes b2r_search_batch use the plain "score everything, then select" path
  * instead of the fused-selection path (both are exact). */
 void b2r_set_fused_selection(int enabled);
-/* Test / profiling hook: 0 = the scorer ignores the slabs of an index (results are identical). */
-void b2r_set_slabs(int enabled);
 /* Test / profiling hook: 0 = later index builds keep dense segments doc-ascending (no bank schedule). */
 void b2r_set_bank_schedule(int enabled);
 

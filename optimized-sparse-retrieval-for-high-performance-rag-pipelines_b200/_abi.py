@@ -34,9 +34,7 @@ class B2RIndex(C.Structure):
         ("dense_id", C.c_void_p),
         ("dense_ptr", C.c_void_p),
         ("n_dense_max", C.c_int32),
-        ("n_slabs", C.c_int32),
-        ("slab_idx", C.c_void_p),
-        ("slab_val", C.c_void_p),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -49,7 +47,6 @@ class B2RIndexSizes(C.Structure):
         ("dense_id_bytes", C.c_size_t),
         ("dense_ptr_bytes", C.c_size_t),
         ("n_dense_max", C.c_int64),
-        ("slab_idx_bytes", C.c_size_t),
     ]
 
 
@@ -57,7 +54,7 @@ class B2RFileSection(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("bytes", C.c_uint64), ("checksum", C.c_uint64)]
 
 
-SEC_NAMES = ("post_doc", "post_val", "blk_ptr", "dense_id", "dense_ptr", "idf", "slab_idx", "slab_val")   # B2R_SEC_* order
+SEC_NAMES = ("post_doc", "post_val", "blk_ptr", "dense_id", "dense_ptr", "idf")   # B2R_SEC_* order
 FILE_ALIGN = 4096
 
 
@@ -76,12 +73,10 @@ class B2RIndexFileHeader(C.Structure):
         ("kind", C.c_int32),
         ("n_dense_max", C.c_int32),
         ("subtiles", C.c_int32),
-        ("n_slabs", C.c_int32),
-        ("reserved1", C.c_int32),
         ("k1", C.c_double),
         ("b", C.c_double),
         ("avgdl", C.c_double),
-        ("sections", B2RFileSection * 8),
+        ("sections", B2RFileSection * 6),
     ]
 
 
@@ -97,10 +92,6 @@ SIGNATURES = {
     "b2r_index_sizes_for": (C.c_int, [_I64, _I64, _I32, _I32, _I32, C.POINTER(B2RIndexSizes)]),
     "b2r_index_build": (C.c_int, [_PIX, _P, _P, _P, _P, _F64, _F64, _F64, _P, _SZ, _P]),
     "b2r_index_build_status": (C.c_int, [_P, _P]),
-    "b2r_index_slab_count": (C.c_int, [_P, _P, C.POINTER(_I32)]),
-    "b2r_index_slab_bytes": (_SZ, [_I32, _I32, _I32]),
-    "b2r_index_build_slabs": (C.c_int, [_PIX, _P]),
-    "b2r_set_slabs": (None, [C.c_int]),
     "b2r_checksum64": (C.c_uint64, [_P, _SZ]),
     "b2r_index_file_layout": (C.c_int, [C.POINTER(B2RIndexFileHeader), C.POINTER(C.c_uint64)]),
     "b2r_index_file_check": (C.c_int, [C.POINTER(B2RIndexFileHeader), C.c_uint64]),

@@ -379,128 +379,6 @@ bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__res
     }
 }
 
-// ---- pass 5b: head rows ---------------------------------------------------------------------------------
-// The B2R_HEAD_TERMS dense terms with the largest df are moved to rows 0 .. B2R_HEAD_TERMS-1 of the dense table
-// (rows are handed out by an atomic counter, so this is a swap of row numbers between two terms).  One CTA.
-__global__ void __launch_bounds__(BLD_THREADS)
-dense_head_kernel(const uint32_t *__restrict__ blk_ptr, int32_t n_vocab, int n_tiles, int32_t n_dense_max,
-                  int32_t *__restrict__ dense_id, const int32_t *__restrict__ counter, int32_t *__restrict__ row_term,
-                  uint32_t *__restrict__ row_df) {
-    __shared__ unsigned long long best[BLD_THREADS / 32];
-    __shared__ unsigned long long chosen;
-    const int n_dense = min(*counter, n_dense_max);
-    for (int32_t t = threadIdx.x; t < n_vocab; t += blockDim.x) {
-        const int32_t id = dense_id[t];
-        if (id >= 0) {
-            row_term[id] = t;
-            row_df[id] = blk_ptr[(size_t)(t + 1) * n_tiles] - blk_ptr[(size_t)t * n_tiles];
-        }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int h = 0; h < B2R_HEAD_TERMS && h < n_dense; ++h) {
-        // argmax over rows h .. n_dense-1 of (df, then the smaller term id): key = df << 32 | ~term
-        unsigned long long m = 0;
-        for (int r = h + threadIdx.x; r < n_dense; r += blockDim.x) {
-            const unsigned long long key = ((unsigned long long)row_df[r] << 32) | (uint32_t)(0x7FFFFFFF - row_term[r]);
-            // the row number rides along in a second reduction: keep (key, row) by comparing keys only
-            if (key > m) m = key;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o);
-            if (x > m) m = x;
-        }
-        if (lane == 0) best[wid] = m;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long x = 0;
-            for (int i = 0; i < BLD_THREADS / 32; ++i) x = best[i] > x ? best[i] : x;
-            chosen = x;
-        }
-        __syncthreads();
-        const int32_t want_term = 0x7FFFFFFF - (int32_t)(uint32_t)(chosen & 0xFFFFFFFFull);
-        // the thread that holds the chosen row performs the swap (terms are unique per row)
-        for (int r = h + threadIdx.x; r < n_dense; r += blockDim.x) {
-            if (row_term[r] == want_term) {
-                const int32_t other_term = row_term[h];
-                const uint32_t other_df = row_df[h];
-                row_term[h] = want_term;
-                row_df[h] = row_df[r];
-                if (r != h) {
-                    row_term[r] = other_term;
-                    row_df[r] = other_df;
-                    dense_id[other_term] = r;
-                }
-                dense_id[want_term] = h;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---- pass 7: slabs ----------------------------------------------------------------------------------
-// A (dense term, sub-tile) segment with postings for a large share of the sub-tile's documents is ALSO stored as a
-// slab: the sub-tile's values in document order, 0 where a document has no posting (include/b200ret.h, b2r_index).
-// Marking (here, inside b2r_index_build) only numbers the slabs; the values are filled by b2r_index_build_slabs once
-// the caller has allocated exactly n_slabs of them.  grid = (dense rows, segment chunks).
-__global__ void __launch_bounds__(BLD_THREADS)
-slab_mark_kernel(const uint32_t *__restrict__ dense_ptr, int n_tiles, int32_t n_dense_max, const int32_t *__restrict__ n_dense,
-                 uint32_t slab_min, int32_t *__restrict__ slab_idx, int32_t *__restrict__ counter) {
-    const int nd = min(*n_dense, n_dense_max);
-    const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
-    for (int h = blockIdx.x; h < nd; h += gridDim.x) {
-        const uint32_t *row = dense_ptr + (size_t)h * (n_seg + 1);
-        int32_t *out = slab_idx + (size_t)h * n_seg;
-        for (size_t seg = (size_t)blockIdx.y * blockDim.x + threadIdx.x; seg < n_seg; seg += (size_t)gridDim.y * blockDim.x) {
-            const uint32_t n = row[seg + 1] - row[seg];
-            out[seg] = n >= slab_min ? atomicAdd(counter, 1) : -1;
-        }
-    }
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(BLD_THREADS)
-slab_fill_kernel(const uint32_t *__restrict__ dense_ptr, const int32_t *__restrict__ slab_idx, int n_tiles, int tile_docs,
-                 int32_t n_dense_max, int32_t n_slabs, const uint32_t *__restrict__ post_doc,
-                 const void *__restrict__ post_val, void *__restrict__ slab_val) {
-    using val_t = typename std::conditional<KIND == B2R_KIND_BM25, double, float>::type;
-    const int lane = threadIdx.x & 31, n_warps = (gridDim.y * BLD_THREADS) / 32;
-    const int wib = (blockIdx.y * BLD_THREADS + threadIdx.x) >> 5;
-    const int sub = tile_docs / B2R_SUBTILES;
-    const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
-    const val_t *src = static_cast<const val_t *>(post_val);
-    val_t *dst = static_cast<val_t *>(slab_val);
-    for (int h = blockIdx.x; h < n_dense_max; h += gridDim.x) {
-        const uint32_t *row = dense_ptr + (size_t)h * (n_seg + 1);
-        const int32_t *sid_row = slab_idx + (size_t)h * n_seg;
-        for (size_t seg = wib; seg < n_seg; seg += n_warps) {
-            const int32_t sid = sid_row[seg];   // (-1 in rows no term owns: the table was preset)
-            if (sid < 0 || sid >= n_slabs) continue;
-            const uint32_t lo = row[seg], hi = row[seg + 1];
-            const uint32_t doc0 = (uint32_t)seg * (uint32_t)sub;
-            for (uint32_t p = lo + lane; p < hi; p += 32) {
-                const uint32_t l = post_doc[p] - doc0;
-                if (l < (uint32_t)sub) dst[(size_t)sid * sub + l] = src[p];
-            }
-        }
-    }
-}
-
-// share of a sub-tile's documents from which a segment gets a slab (B2R_SLAB_MIN_FRAC overrides it: tuning only; a
-// value above 1 turns slabs off).  Slabs exist for sub-tiles of >= 256 documents (tile_docs >= B2R_SLAB_TILE_DOCS).
-static uint32_t slab_min_postings(int tile_docs) {
-    static const double frac = [] {
-        const char *e = getenv("B2R_SLAB_MIN_FRAC");
-        const double x = e ? atof(e) : 0.0;
-        return x > 0.0 ? x : (double)B2R_SLAB_MIN_NUM / B2R_SLAB_MIN_DEN;
-    }();
-    if (tile_docs < B2R_SLAB_TILE_DOCS) return 0xFFFFFFFFu;
-    const double m = frac * (tile_docs / B2R_SUBTILES);
-    if (m > (double)(tile_docs / B2R_SUBTILES)) return 0xFFFFFFFFu;
-    return m < 1.0 ? 1u : (uint32_t)(m + 0.999999);
-}
-
 static bool g_bank_schedule = true;
 
 // postings per tile from which a term gets sub-tile offsets (B2R_DENSE_MIN overrides it: tuning experiments only)
@@ -541,7 +419,6 @@ extern "C" int b2r_index_sizes_for(int64_t nnz, int64_t n_docs, int32_t n_vocab,
     out->n_dense_max = nnz / ((int64_t)b2r::dense_min_per_tile() * n_tiles) + 1;
     out->dense_id_bytes = align_up((size_t)n_vocab * 4, 256);
     out->dense_ptr_bytes = align_up((size_t)out->n_dense_max * ((size_t)n_tiles * B2R_SUBTILES + 1) * 4, 256);
-    out->slab_idx_bytes = align_up((size_t)out->n_dense_max * (size_t)n_tiles * B2R_SUBTILES * 4, 256);
     return B2R_OK;
 }
 
@@ -632,15 +509,6 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
         dense_select_kernel<<<(unsigned)((ix->n_vocab + BLD_THREADS - 1) / BLD_THREADS), BLD_THREADS, 0, st>>>(
             ix->blk_ptr, ix->n_vocab, ix->n_tiles, min_df, ix->n_dense_max, ix->dense_id, counter);
         B2R_LAUNCH_CHECK();
-        {   // head rows: the scratch copy of the postings is dead by now, its space holds the row tables
-            int32_t *row_term = reinterpret_cast<int32_t *>(tmp_doc);
-            uint32_t *row_df = reinterpret_cast<uint32_t *>(tmp_val);
-            if ((size_t)ix->n_dense_max * 4 <= sz.post_doc_bytes && (size_t)ix->n_dense_max * 4 <= sz.post_val_bytes) {
-                dense_head_kernel<<<1, BLD_THREADS, 0, st>>>(ix->blk_ptr, ix->n_vocab, ix->n_tiles, ix->n_dense_max,
-                                                             ix->dense_id, counter, row_term, row_df);
-                B2R_LAUNCH_CHECK();
-            }
-        }
         dense_fill_kernel<<<(unsigned)ix->n_vocab, BLD_THREADS, 0, st>>>(ix->blk_ptr, ix->post_doc, ix->dense_id,
                                                                          ix->n_vocab, ix->n_tiles, ix->tile_docs,
                                                                          ix->dense_ptr);
@@ -663,56 +531,7 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
             }
             B2R_LAUNCH_CHECK();
         }
-        if (ix->slab_idx) {   // number the slab segments (values: b2r_index_build_slabs)
-            int32_t *slab_counter = flag + 2;  // scratch[8..12)
-            B2R_CUDA(cudaMemsetAsync(ix->slab_idx, 0xFF, (size_t)ix->n_dense_max * ix->n_tiles * B2R_SUBTILES * 4, st));
-            const uint32_t slab_min = slab_min_postings(ix->tile_docs);
-            if (slab_min != 0xFFFFFFFFu) {
-                const dim3 mgrid((unsigned)(ix->n_dense_max < 1024 ? ix->n_dense_max : 1024),
-                                 (unsigned)((ix->n_tiles * B2R_SUBTILES + BLD_THREADS - 1) / BLD_THREADS > 16
-                                                ? 16 : (ix->n_tiles * B2R_SUBTILES + BLD_THREADS - 1) / BLD_THREADS));
-                slab_mark_kernel<<<mgrid, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->n_tiles, ix->n_dense_max, counter, slab_min,
-                                                               ix->slab_idx, slab_counter);
-                B2R_LAUNCH_CHECK();
-            }
-        }
     }
-    return B2R_OK;
-}
-
-extern "C" int b2r_index_slab_count(const void *scratch, void *stream, int32_t *n_slabs) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    B2R_CHECK_ARG(scratch && n_slabs, "b2r_index_slab_count: null argument");
-    int32_t n = 0;
-    B2R_CUDA(cudaMemcpyAsync(&n, static_cast<const char *>(scratch) + 8, sizeof(n), cudaMemcpyDeviceToHost, st));
-    B2R_CUDA(cudaStreamSynchronize(st));
-    *n_slabs = n;
-    return B2R_OK;
-}
-
-extern "C" size_t b2r_index_slab_bytes(int32_t n_slabs, int32_t tile_docs, int32_t kind) {
-    const size_t n = n_slabs > 0 ? (size_t)n_slabs : 0;
-    return align_up(n * (size_t)(tile_docs / B2R_SUBTILES) * (kind == B2R_KIND_BM25 ? 8 : 4) + 16, 256);
-}
-
-extern "C" int b2r_index_build_slabs(const b2r_index *ix, void *stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    B2R_CHECK_ARG(ix && ix->post_doc && ix->post_val && ix->dense_id && ix->dense_ptr, "b2r_index_build_slabs: index not built");
-    if (ix->n_slabs <= 0) return B2R_OK;
-    B2R_CHECK_ARG(ix->slab_idx && ix->slab_val, "b2r_index_build_slabs: slab buffers not set");
-    B2R_CHECK_ARG(ix->tile_docs >= B2R_SLAB_TILE_DOCS, "b2r_index_build_slabs: no slabs for tile_docs=%d", ix->tile_docs);
-    B2R_CUDA(cudaMemsetAsync(ix->slab_val, 0, b2r_index_slab_bytes(ix->n_slabs, ix->tile_docs, ix->kind), st));
-    // (rows beyond the number of dense terms hold no slab: slab_idx is -1 there)
-    const dim3 grid((unsigned)(ix->n_dense_max < 2048 ? ix->n_dense_max : 2048), 4);
-    if (ix->kind == B2R_KIND_BM25)
-        slab_fill_kernel<B2R_KIND_BM25><<<grid, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->slab_idx, ix->n_tiles, ix->tile_docs,
-                                                                      ix->n_dense_max, ix->n_slabs, ix->post_doc,
-                                                                      ix->post_val, ix->slab_val);
-    else
-        slab_fill_kernel<B2R_KIND_IMPACT><<<grid, BLD_THREADS, 0, st>>>(ix->dense_ptr, ix->slab_idx, ix->n_tiles, ix->tile_docs,
-                                                                        ix->n_dense_max, ix->n_slabs, ix->post_doc,
-                                                                        ix->post_val, ix->slab_val);
-    B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
 

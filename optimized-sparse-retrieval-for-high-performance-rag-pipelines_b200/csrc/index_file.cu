@@ -20,9 +20,6 @@ static int section_sizes(const b2r_index_file_header *h, uint64_t out[B2R_SEC_CO
     // the dense table is sized by the n_dense_max the index was BUILT with (stored in the header)
     out[B2R_SEC_DENSE_PTR] = align_up((size_t)h->n_dense_max * ((size_t)n_tiles * B2R_SUBTILES + 1) * 4, 256);
     out[B2R_SEC_IDF] = (uint64_t)h->n_vocab * 4;
-    B2R_CHECK_ARG(h->n_slabs >= 0, "index file: bad n_slabs");
-    out[B2R_SEC_SLAB_IDX] = align_up((size_t)h->n_dense_max * (size_t)n_tiles * B2R_SUBTILES * 4, 256);
-    out[B2R_SEC_SLAB_VAL] = b2r_index_slab_bytes(h->n_slabs, h->tile_docs, h->kind);
     return B2R_OK;
 }
 

@@ -42,17 +42,6 @@ __device__ __forceinline__ float ld_stream_f32(const float *p) {
     return v;
 }
 
-__device__ __forceinline__ double2 ld_stream_v2f64(const double2 *p) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float2 ld_stream_v2f32(const float2 *p) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-
 constexpr int SC_THREADS = 32 * B2R_SUBTILES;  // one warp per sub-tile of the CTA's doc tile
 
 // The accumulators are cleared by the copy engine (cp.async.bulk from this zero page), not by stores:
@@ -147,53 +136,6 @@ __device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end
     }
 }
 
-// A slab (include/b200ret.h, b2r_index): the sub-tile's posting values in document order, 0 where the document has
-// no posting.  Lane l handles documents {64 c + 2 l, 64 c + 2 l + 1}: one coalesced 16-byte load brings two values,
-// the accumulators are read and written 16 bytes at a time (conflict-free by construction) and no document id is
-// loaded at all -- about 5 instructions per 32 documents where the posting loop above needs about 24.
-// acc += (idf * 0) * q leaves acc bit-identical (acc is never -0.0: it starts at +0.0), so absent documents need no
-// mask; terms with a non-finite weight never take this path (see the staging code).  FIRST: the sub-tile has not
-// been touched (and not been cleared): every accumulator is written.
-#ifndef SC_SLAB_BATCH
-#define SC_SLAB_BATCH 4   // 16-byte slab loads in flight per lane
-#endif
-template <int KIND, bool FIRST>
-__device__ __forceinline__ void apply_slab(double *acc_w, const void *__restrict__ slab_val, int32_t slab, int sub, int lane,
-                                           float w_idf, float w_q) {
-    double *a_l = acc_w + 2 * lane;
-    if (KIND == B2R_KIND_BM25) {
-        const double2 *sv = static_cast<const double2 *>(slab_val) + (size_t)slab * (size_t)(sub >> 1) + lane;
-        const double wi = (double)w_idf, wq = (double)w_q;
-        for (int c0 = 0; c0 < (sub >> 6); c0 += SC_SLAB_BATCH) {   // (slabs exist for sub-tiles of >= 256 documents)
-            double2 u[SC_SLAB_BATCH];
-#pragma unroll
-            for (int c = 0; c < SC_SLAB_BATCH; ++c) u[c] = ld_stream_v2f64(sv + 32 * (c0 + c));
-#pragma unroll
-            for (int c = 0; c < SC_SLAB_BATCH; ++c) {
-                double2 a = FIRST ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(a_l + 64 * (c0 + c));
-                a.x = __dadd_rn(a.x, __dmul_rn(__dmul_rn(wi, u[c].x), wq));
-                a.y = __dadd_rn(a.y, __dmul_rn(__dmul_rn(wi, u[c].y), wq));
-                *reinterpret_cast<double2 *>(a_l + 64 * (c0 + c)) = a;
-            }
-        }
-    } else {
-        const float2 *sv = static_cast<const float2 *>(slab_val) + (size_t)slab * (size_t)(sub >> 1) + lane;
-        for (int c0 = 0; c0 < (sub >> 6); c0 += SC_SLAB_BATCH) {
-            float2 u[SC_SLAB_BATCH];
-#pragma unroll
-            for (int c = 0; c < SC_SLAB_BATCH; ++c) u[c] = ld_stream_v2f32(sv + 32 * (c0 + c));
-#pragma unroll
-            for (int c = 0; c < SC_SLAB_BATCH; ++c) {
-                double2 a = FIRST ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(a_l + 64 * (c0 + c));
-                // reference (fastmath) evaluates (tf * qtf) * idf in f32, then widens
-                a.x = __dadd_rn(a.x, (double)__fmul_rn(__fmul_rn(u[c].x, w_q), w_idf));
-                a.y = __dadd_rn(a.y, (double)__fmul_rn(__fmul_rn(u[c].y, w_q), w_idf));
-                *reinterpret_cast<double2 *>(a_l + 64 * (c0 + c)) = a;
-            }
-        }
-    }
-}
-
 // One CTA = one (query, doc tile); one WARP = one sub-tile of tile_docs/8 docs whose f64 accumulators
 // it alone touches.  A warp applies the query's terms in ascending term id to its own sub-tile, so the
 // only synchronisation is __syncwarp: no CTA barrier, no atomics, no load imbalance between warps
@@ -221,13 +163,12 @@ struct ScoreOut {
 
 template <int KIND, int OUT>
 #ifndef SC_MIN_CTAS
-#define SC_MIN_CTAS 5  // 6 CTAs/SM is what 32 KB of accumulators per CTA allows (40 registers per thread)
+#define SC_MIN_CTAS 6  // 6 CTAs/SM is what 32 KB of accumulators per CTA allows (40 registers per thread)
 #endif
 __global__ void __launch_bounds__(SC_THREADS, SC_MIN_CTAS)
 score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict__ post_val,
                    const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
-                   const uint32_t *__restrict__ dense_ptr, const int32_t *__restrict__ slab_idx,
-                   const void *__restrict__ slab_val, int n_tiles, int tile_docs,
+                   const uint32_t *__restrict__ dense_ptr, int n_tiles, int tile_docs,
                    const int32_t *__restrict__ q_ptr, const int32_t *__restrict__ q_terms,
                    const float *__restrict__ q_weights, const float *__restrict__ idf, int q0, int tile_mode,
                    int tile_step, int n_y, ScoreOut o) {
@@ -240,8 +181,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap) return;
     const int sub = tile_docs / B2R_SUBTILES;
     double *acc_w = acc + w * sub;
-    const size_t n_seg = (size_t)n_tiles * B2R_SUBTILES;
-    const size_t dense_row = n_seg + 1;
+    const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
     const uint32_t zbar_a = sc_smem_u32(&zbar[w]);
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(zbar_a) : "memory");
@@ -259,11 +199,9 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     // per CTA instead of once per tile.
     const bool staged = qe - qs <= 32;
     const uint32_t *my_row = nullptr;  // dense: offsets per sub-tile; sparse: offsets per tile
-    const int32_t *my_slab_row = nullptr;  // dense term with usable slabs: slab numbers per sub-tile
     typename TermW<KIND>::type my_idf = 0, my_qw = 0;
     int my_dense = 0;
     uint32_t nxt_beg = 0, nxt_end = 0;
-    int32_t nxt_slab = -1;
     if (staged && lane < qe - qs) {
         const int t = q_terms[qs + lane];
         my_qw = q_weights[qs + lane];
@@ -271,25 +209,14 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         const int32_t did = dense_id[t];
         my_dense = did >= 0;
         my_row = my_dense ? dense_ptr + (size_t)did * dense_row + w : blk_ptr + (size_t)t * n_tiles;
-        // slabs add (idf * 0) * q for absent documents: only exact when both weights are finite
-        if (slab_idx != nullptr && my_dense && isfinite((float)my_idf) && isfinite((float)my_qw))
-            my_slab_row = slab_idx + (size_t)did * n_seg + w;
         if ((int)blockIdx.y < n_y) {
             const size_t i0 = (size_t)tile_of(blockIdx.y) * (my_dense ? B2R_SUBTILES : 1);
             nxt_beg = my_row[i0];
             nxt_end = my_row[i0 + 1];
-            if (my_slab_row != nullptr) nxt_slab = my_slab_row[i0];
         }
     }
   for (int y = blockIdx.y; y < n_y; y += gridDim.y) {
-    // The sub-tile needs no clearing when the first term that touches it is a slab (it writes every accumulator).
-    bool need_clear = true;
-    if (staged) {
-        const unsigned nonempty = __ballot_sync(full, nxt_beg != nxt_end);
-        const unsigned slabm = __ballot_sync(full, nxt_slab >= 0);
-        need_clear = nonempty == 0 || !((slabm >> (__ffs(nonempty) - 1)) & 1u);
-    }
-    if (need_clear && lane == 0) {  // clear my sub-tile's accumulators with one bulk copy; overlaps the term staging below
+    if (lane == 0) {  // clear my sub-tile's accumulators with one bulk copy; overlaps the term staging below
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar_a), "r"((uint32_t)(sub * 8))
                      : "memory");
         asm volatile(
@@ -302,15 +229,13 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
     const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
     uint32_t my_beg = nxt_beg, my_end = nxt_end;
-    int32_t my_slab = nxt_slab;
     if (staged && my_row != nullptr && y + (int)gridDim.y < n_y) {  // offsets of the next tile: used one iteration later
         const size_t i1 = (size_t)tile_of(y + gridDim.y) * (my_dense ? B2R_SUBTILES : 1);
         nxt_beg = my_row[i1];
         nxt_end = my_row[i1 + 1];
-        if (my_slab_row != nullptr) nxt_slab = my_slab_row[i1];
     }
 
-    bool cleared = !need_clear;
+    bool cleared = false;
     bool first = true;  // no term has touched this warp's sub-tile yet (warp-uniform)
 
     for (int j0 = qs; j0 < qe; j0 += 32) {
@@ -318,7 +243,6 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         if (!staged) {  // long query: lane j stages term j0+j for this tile (dense: my sub-tile; sparse: the tile block)
             my_beg = my_end = 0;
             my_dense = 0;
-            my_slab = -1;
             if (lane < nt) {
                 const int t = q_terms[j0 + lane];
                 my_qw = q_weights[j0 + lane];
@@ -329,8 +253,6 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
                     my_beg = row[0];
                     my_end = row[1];
                     my_dense = 1;
-                    if (slab_idx != nullptr && isfinite((float)my_idf) && isfinite((float)my_qw))
-                        my_slab = slab_idx[(size_t)did * n_seg + my_sub];
                 } else {
                     const size_t e = (size_t)t * n_tiles + tile;
                     my_beg = blk_ptr[e];
@@ -347,21 +269,15 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             if (beg == end) continue;  // warp-uniform
             const int dense = __shfl_sync(full, my_dense, j);
             const typename TermW<KIND>::type w_idf = __shfl_sync(full, my_idf, j), w_q = __shfl_sync(full, my_qw, j);
-            const int32_t slab = __shfl_sync(full, my_slab, j);
-            if (slab >= 0) {
-                if (first) apply_slab<KIND, true>(acc_w, slab_val, slab, sub, lane, (float)w_idf, (float)w_q);
-                else apply_slab<KIND, false>(acc_w, slab_val, slab, sub, lane, (float)w_idf, (float)w_q);
-            } else {
-                if (first) apply_term<KIND, true>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
-                else apply_term<KIND, false>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
-            }
+            if (first) apply_term<KIND, true>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
+            else apply_term<KIND, false>(dense, beg, end, lane, sub, my_doc0, post_doc, post_val, acc_w, w_idf, w_q);
             first = false;
             __syncwarp();
         }
     }
 
     if (!cleared) sc_mbar_wait(zbar_a, zphase);  // query without terms
-    if (need_clear) zphase ^= 1;
+    zphase ^= 1;
     if (OUT == SC_OUT_DENSE) {
         float *out = o.scores + (int64_t)ql * o.scores_stride + (int64_t)y * tile_docs + w * sub;
         for (int i = lane * 2; i < sub; i += 64) {
@@ -432,7 +348,6 @@ static int tiles_per_cta_default() {
     return v >= 1 && v <= 64 ? v : 4;
 }
 static const int g_tiles_per_cta = tiles_per_cta_default();
-static bool g_slabs_enabled = true;   // b2r_set_slabs: test / profiling hook (same results either way)
 
 template <int OUT>
 static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
@@ -445,21 +360,18 @@ static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int
     while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 6 * 4) per_cta >>= 1;
     const int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
     dim3 grid((unsigned)nq, (unsigned)grid_y);
-    // slabs: sub-tiles of >= 256 documents (the slab loop moves 4 x 64 documents per step)
-    const int32_t *slabs = (g_slabs_enabled && ix->slab_idx && ix->slab_val && ix->n_slabs > 0 && ix->tile_docs >= 2048)
-                               ? ix->slab_idx : nullptr;
     if (ix->kind == B2R_KIND_BM25) {
         auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;
         B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
-                                               slabs, ix->slab_val, ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms,
-                                               L.q_weights, L.idf, q0, tile_mode, tile_step, n_y, o);
+                                               ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms, L.q_weights, L.idf, q0,
+                                               tile_mode, tile_step, n_y, o);
     } else {
         auto kern = score_tiles_kernel<B2R_KIND_IMPACT, OUT>;
         B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SC_THREADS, smem, L.st>>>(ix->post_doc, ix->post_val, ix->blk_ptr, ix->dense_id, ix->dense_ptr,
-                                               slabs, ix->slab_val, ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms,
-                                               L.q_weights, L.idf, q0, tile_mode, tile_step, n_y, o);
+                                               ix->n_tiles, ix->tile_docs, L.q_ptr, L.q_terms, L.q_weights, L.idf, q0,
+                                               tile_mode, tile_step, n_y, o);
     }
     B2R_LAUNCH_CHECK();
     return B2R_OK;
@@ -529,8 +441,6 @@ using namespace b2r;
 
 // test / profiling hook: 0 disables the fused-selection path (plain score + select is used)
 extern "C" void b2r_set_fused_selection(int enabled) { b2r::g_fused_enabled = enabled != 0; }
-// test / profiling hook: 0 makes the scorer ignore an index's slabs (posting lists only)
-extern "C" void b2r_set_slabs(int enabled) { b2r::g_slabs_enabled = enabled != 0; }
 
 extern "C" int b2r_set_profiling(int enabled) {
     if (enabled && !g_ev[0]) {

@@ -11,11 +11,6 @@ libb200ret.so through the C ABI.  The doc-major scipy CSR the reference builds
   blk_ptr   u32[V*T+1] postings of (term t, tile T) are [blk_ptr[t*T_n+T], blk_ptr[t*T_n+T+1]), doc-ascending
   dense_id  i32[V]     row of dense_ptr for terms averaging >= 64 postings per tile, else -1
   dense_ptr u32[...]   per dense term: offsets of its postings per sub-tile (8 sub-tiles per tile)
-  slab_idx  i32[8*T*8] per head term (the 8 dense terms with the largest df = dense rows 0..7) and sub-tile: number
-                       of the segment's slab, or -1
-  slab_val  f64|f32    slabs: a sub-tile's posting values in document order (0 = no posting), for the head-term
-                       segments that cover >= 1/4 of their sub-tile (tile_docs == 2048).  The scorer copies a doc
-                       tile's slabs into shared memory once per CTA and applies them to register accumulators
   idf       f32[V]
 """
 from __future__ import annotations
@@ -116,7 +111,6 @@ class TermMajorIndex:
         self.b = 0.75
         self.avgdl = 0.0
         self.idf_host: Optional[np.ndarray] = None
-        self.n_slabs = 0
         self._desc = _abi.B2RIndex()
         self._bufs = {}
         # Concurrency (the reference's search_bm25 may be called from several threads): the workspace is kept per
@@ -131,7 +125,7 @@ class TermMajorIndex:
     @classmethod
     def from_csr(cls, data, indices, indptr, doc_lengths=None, *, n_vocab: int, idf=None, avgdl=None,
                  k1: float = 1.2, b: float = 0.75, kind: str = "bm25", doc_id_base: int = 0,
-                 tile_docs: int = 2048, device=None) -> "TermMajorIndex":
+                 tile_docs: int = 4096, device=None) -> "TermMajorIndex":
         """Build from a doc-major CSR (numpy arrays or CUDA tensors).
 
         idf / avgdl default to the reference's host expressions over THIS CSR; a doc-sharded build
@@ -173,7 +167,6 @@ class TermMajorIndex:
         b_["blk_ptr"] = torch.empty(sizes.blk_ptr_bytes, dtype=torch.uint8, device=dev)
         b_["dense_id"] = torch.empty(sizes.dense_id_bytes, dtype=torch.uint8, device=dev)
         b_["dense_ptr"] = torch.empty(sizes.dense_ptr_bytes, dtype=torch.uint8, device=dev)
-        b_["slab_idx"] = torch.empty(sizes.slab_idx_bytes, dtype=torch.uint8, device=dev)
         b_["idf"] = torch.from_numpy(self.idf_host).to(dev)
         scratch = torch.empty(sizes.scratch_bytes, dtype=torch.uint8, device=dev)
 
@@ -182,7 +175,6 @@ class TermMajorIndex:
         d.n_vocab, d.tile_docs, d.n_tiles, d.kind = self.n_vocab, self.tile_docs, self.n_tiles, kind_id
         d.post_doc, d.post_val, d.blk_ptr = b_["post_doc"].data_ptr(), b_["post_val"].data_ptr(), b_["blk_ptr"].data_ptr()
         d.dense_id, d.dense_ptr, d.n_dense_max = b_["dense_id"].data_ptr(), b_["dense_ptr"].data_ptr(), int(sizes.n_dense_max)
-        d.slab_idx, d.slab_val, d.n_slabs = b_["slab_idx"].data_ptr(), None, 0
 
         # stage the CSR on the device (freed after the build)
         tf_d = _to_device(data, torch.float32, dev)
@@ -195,15 +187,7 @@ class TermMajorIndex:
                                             self.avgdl if kind == "bm25" else 1.0, scratch.data_ptr(),
                                             scratch.numel(), st), "index build")
         _abi.check(_abi.lib.b2r_index_build_status(scratch.data_ptr(), st), "index build")
-        # slabs: the build numbered the segments that qualify; allocate exactly that many and fill them
-        n_slabs = C.c_int32(0)
-        _abi.check(_abi.lib.b2r_index_slab_count(scratch.data_ptr(), st, C.byref(n_slabs)), "slab count")
         del tf_d, ind_d, ptr_d, dl_d, scratch
-        b_["slab_val"] = torch.empty(int(_abi.lib.b2r_index_slab_bytes(n_slabs.value, self.tile_docs, kind_id)),
-                                     dtype=torch.uint8, device=dev)
-        d.slab_val, d.n_slabs = b_["slab_val"].data_ptr(), int(n_slabs.value)
-        _abi.check(_abi.lib.b2r_index_build_slabs(C.byref(d), st), "slab build")
-        self.n_slabs = int(n_slabs.value)
         return self
 
     # ------------------------------------------------------------------ on-disk form
@@ -211,14 +195,13 @@ class TermMajorIndex:
 
     def save(self, path) -> int:
         """Write the HBM layout verbatim to `path` (format: include/b200ret.h, b2r_index_file_header): a 4096-byte
-        header, then post_doc / post_val / blk_ptr / dense_id / dense_ptr / idf / slab_idx / slab_val, each 4096-aligned and
+        header, then post_doc / post_val / blk_ptr / dense_id / dense_ptr / idf, each 4096-aligned and
         checksummed.  The reference can only cache the doc-major CSR (.npz, evaluate_rag_pipeline.py:280-312)
         and rebuilds everything else on load; this file goes back to HBM with no re-layout.  Returns the file size."""
         hdr = _abi.B2RIndexFileHeader()
         d = self._desc
         hdr.n_docs, hdr.doc_id_base, hdr.nnz = d.n_docs, d.doc_id_base, d.nnz
         hdr.n_vocab, hdr.tile_docs, hdr.kind, hdr.n_dense_max = d.n_vocab, d.tile_docs, d.kind, d.n_dense_max
-        hdr.n_slabs = d.n_slabs
         hdr.k1, hdr.b, hdr.avgdl = self.k1, self.b, self.avgdl
         total = C.c_uint64(0)
         _abi.check(_abi.lib.b2r_index_file_layout(C.byref(hdr), C.byref(total)), "index file layout")
@@ -291,8 +274,6 @@ class TermMajorIndex:
         d.n_vocab, d.tile_docs, d.n_tiles, d.kind = self.n_vocab, self.tile_docs, self.n_tiles, int(hdr.kind)
         d.post_doc, d.post_val, d.blk_ptr = b_["post_doc"].data_ptr(), b_["post_val"].data_ptr(), b_["blk_ptr"].data_ptr()
         d.dense_id, d.dense_ptr, d.n_dense_max = b_["dense_id"].data_ptr(), b_["dense_ptr"].data_ptr(), int(hdr.n_dense_max)
-        d.slab_idx, d.slab_val, d.n_slabs = b_["slab_idx"].data_ptr(), b_["slab_val"].data_ptr(), int(hdr.n_slabs)
-        self.n_slabs = int(hdr.n_slabs)
         return self
 
     # ------------------------------------------------------------------ properties

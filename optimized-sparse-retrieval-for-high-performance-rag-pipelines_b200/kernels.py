@@ -49,19 +49,13 @@ def set_bank_schedule(enabled: bool) -> None:
     _abi.lib.b2r_set_bank_schedule(1 if enabled else 0)
 
 
-def set_slabs(enabled: bool) -> None:
-    """Profiling / test hook: False makes the scorer ignore the slabs of every index (shared-memory accumulators
-    only).  Results are identical."""
-    _abi.lib.b2r_set_slabs(1 if enabled else 0)
-
-
 def set_int8_fused(mode) -> None:
     """Profiling / test hook: 0/False = plain chunked dense-tile + select path, otherwise the fused-selection
     path (default).  Results are identical."""
     _abi.lib.b2r_set_int8_fused(int(mode))
 
 
-__all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_int8_pair", "set_bank_schedule", "set_slabs", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
+__all__ = ["set_int8_mma", "set_int8_fused", "set_int8_cluster", "set_int8_pair", "set_bank_schedule", "simd_bm25_score", "simd_bm25_batch_score", "fast_topk_selection", "simd_tfidf_score",
            "quantized_dot_product_batch", "optimized_bm25_score", "fast_topk", "clear_index_cache",
            "int8_scan_topk", "int8_rerank", "hybrid_search", "dense_topk"]
 

@@ -53,7 +53,7 @@ class RetrievalService:
         self.query_cache: Dict[str, Tuple[np.ndarray, np.ndarray]] = {}
         self.cache_lock = threading.RLock()
 
-        self.tile_docs = 2048
+        self.tile_docs = 4096
         self._gpu_index: Optional[TermMajorIndex] = None
         self._gpu_params: Optional[tuple] = None
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libb200ret.so does not export {name}"
         assert name in b200ret._abi.SIGNATURES, f"_abi.py does not bind {name}"
-    assert lib.b2r_version() == 101
+    assert lib.b2r_version() == 100
 
 
 def test_sizes_and_argument_errors_without_a_gpu():
@@ -75,10 +75,10 @@ def test_index_file_header_layout_and_validation():
         return h, total.value
 
     h, total = fresh()
-    assert h.magic == b"B2RIDX01" and h.version == 2 and h.header_bytes == 4096 and h.n_tiles == 10 and h.subtiles == 8
+    assert h.magic == b"B2RIDX01" and h.version == 1 and h.header_bytes == 4096 and h.n_tiles == 10 and h.subtiles == 8
     sizes = _abi.B2RIndexSizes()
     assert lib.b2r_index_sizes_for(123_456, 10_000, 777, 1024, 0, C.byref(sizes)) == 0
-    want = [sizes.post_doc_bytes, sizes.post_val_bytes, sizes.blk_ptr_bytes, sizes.dense_id_bytes, None, 777 * 4, None, 256]
+    want = [sizes.post_doc_bytes, sizes.post_val_bytes, sizes.blk_ptr_bytes, sizes.dense_id_bytes, None, 777 * 4]
     end = 4096
     for i, sec in enumerate(h.sections):
         assert sec.offset % 4096 == 0 and sec.offset >= end and (want[i] is None or sec.bytes == want[i])
@@ -93,7 +93,7 @@ def test_index_file_header_layout_and_validation():
         return rc == -5 and len(lib.b2r_last_error()) > 0
 
     assert rejected(lambda g: setattr(g, "magic", b"NOTANIDX"))
-    assert rejected(lambda g: setattr(g, "version", 1))
+    assert rejected(lambda g: setattr(g, "version", 2))
     assert rejected(lambda g: setattr(g, "n_tiles", 11))
     assert rejected(lambda g: setattr(g, "tile_docs", 1000))                 # not a power of two
     assert rejected(lambda g: setattr(g.sections[1], "bytes", g.sections[1].bytes - 8))

@@ -761,118 +761,3 @@ def test_full_size_1m_docs_properties(b2r):
                                                      ws.data_ptr(), ws.numel(),
                                                      int(torch.cuda.current_stream().cuda_stream)))
     assert torch.equal(mi, idx) and torch.equal(mv, val)
-
-
-# ----------------------------------------------------------------------------------- slabs (register accumulators)
-@pytest.mark.parametrize("kind", ["bm25", "impact"])
-@pytest.mark.parametrize("tile_docs", [2048, 4096])
-def test_slab_path_equals_posting_path_and_oracle(b2r, kind, tile_docs):
-    """Dense-term segments covering >= 1/4 of a sub-tile also exist as slabs (values in document order, 0 = no
-    posting), which the scorer streams instead of the posting list.  Checked: (1) the 8 dense terms with the largest df
-    own dense rows 0..7 and the slabs hold exactly the postings of their segment, 0 elsewhere; (2) dense scores, fused
-    and plain top-k are bit-identical with slabs on and off and equal the oracle.  The vocabulary is partly REVERSED
-    for half of the runs, so that head terms carry large ids: sparse terms then come first, the sub-tile is cleared
-    and the slab path does read-modify-write instead of its first-term store."""
-    from b200ret import synthetic as S
-    n_docs, n_vocab, k = 70_000 + 13, 6000, 10
-    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 60, seed=51)
-    rng = np.random.default_rng(52)
-    for reverse in (False, True):
-        if reverse:
-            rows = np.repeat(np.arange(n_docs), np.diff(indptr))
-            # odd ranks go to the top of the vocabulary, even ranks stay: dense and sparse terms interleave
-            t = indices.astype(np.int64)
-            t = np.where(t % 2 == 1, n_vocab - t, t)          # (n_vocab is even: odd ids map onto odd ids)
-            order = np.lexsort((t, rows))
-            ind2, dat2 = t[order].astype(np.int32), data[order]
-            assert all(len(set(ind2[indptr[d]:indptr[d + 1]].tolist())) == indptr[d + 1] - indptr[d] for d in range(50))
-        else:
-            ind2, dat2 = indices, data
-        if kind == "impact":
-            dat2 = (dat2 * rng.random(len(dat2)).astype(np.float32) + np.float32(0.01)).astype(np.float32)
-        idf = b2r.reference_idf(ind2, n_docs, n_vocab) if kind == "bm25" else rng.random(n_vocab).astype(np.float32) + 0.5
-        avgdl = b2r.reference_avgdl(dl)
-        df = np.bincount(ind2, minlength=n_vocab)
-        head = np.argsort(-df)[:12]
-        qs = []
-        for i in range(96):
-            nt = int(rng.integers(1, 8))
-            terms = set(rng.choice(head, size=min(nt, int(rng.integers(0, 4))), replace=False).tolist())
-            terms |= set(rng.integers(0, n_vocab, nt).tolist())
-            terms = sorted(terms)
-            qs.append((terms, (rng.integers(1, 4, len(terms))).astype(np.float32)))
-        qs.append((sorted(head.tolist()), np.ones(len(head), np.float32)))          # slab terms only
-        q_ptr, q_terms, q_w = b2r.pack_queries(qs)
-        ix = b2r.TermMajorIndex.from_csr(dat2, ind2, indptr, dl if kind == "bm25" else None, n_vocab=n_vocab, idf=idf,
-                                         avgdl=avgdl, tile_docs=tile_docs, kind=kind)
-        assert ix.n_slabs > 20
-        # (1) slab contents
-        sub, n_seg = tile_docs // 8, ix.n_tiles * 8
-        did = ix._bufs["dense_id"].view(torch.int32)[:n_vocab].cpu().numpy()
-        dptr = ix._bufs["dense_ptr"].view(torch.int32).cpu().numpy().astype(np.int64)
-        sidx = ix._bufs["slab_idx"].view(torch.int32).cpu().numpy()
-        vdt = torch.float64 if kind == "bm25" else torch.float32
-        sval = ix._bufs["slab_val"].view(vdt)[:ix.n_slabs * sub].cpu().numpy().reshape(ix.n_slabs, sub)
-        pdoc = ix._bufs["post_doc"].view(torch.int32)[:len(ind2)].cpu().numpy().astype(np.int64)
-        pval = ix._bufs["post_val"].view(vdt)[:len(ind2)].cpu().numpy()
-        seen = 0
-        assert len(set(df[head[:9]].tolist())) == 9            # (distinct dfs: the head rows are unambiguous)
-        assert did[head[:8]].tolist() == list(range(8)) and (did[head[8:]] >= 8).all()
-        for t in head[:6]:
-            row = dptr[did[t] * (n_seg + 1):(did[t] + 1) * (n_seg + 1)]
-            for sg in range(n_seg):
-                lo, hi = row[sg], row[sg + 1]
-                s_ = sidx[did[t] * n_seg + sg]
-                assert (s_ >= 0) == (hi - lo >= sub // 4), (t, sg)
-                if s_ >= 0:
-                    want = np.zeros(sub, sval.dtype)
-                    want[pdoc[lo:hi] - sg * sub] = pval[lo:hi]
-                    assert np.array_equal(sval[s_].view(np.uint8), want.view(np.uint8)), (t, sg)
-                    seen += 1
-        assert seen > 10
-        # (2) results
-        out = {}
-        for on in (True, False):
-            b2r.set_slabs(on)
-            try:
-                s = ix.score_dense(q_ptr, q_terms, q_w).cpu().numpy()
-                fi, fv = ix.search(q_ptr, q_terms, q_w, k)
-                b2r.set_fused_selection(False)
-                pi, pv = ix.search(q_ptr, q_terms, q_w, k)
-            finally:
-                b2r.set_fused_selection(True)
-                b2r.set_slabs(True)
-            assert torch.equal(fi, pi) and torch.equal(fv, pv)
-            out[on] = (s, fi.cpu().numpy(), fv.cpu().numpy())
-        assert np.array_equal(_bits(out[True][0]), _bits(out[False][0]))
-        assert np.array_equal(out[True][1], out[False][1]) and np.array_equal(_bits(out[True][2]), _bits(out[False][2]))
-        for q in range(0, len(qs), 7):
-            qtf = np_oracle.dense_query(q_terms[q_ptr[q]:q_ptr[q + 1]], q_w[q_ptr[q]:q_ptr[q + 1]], n_vocab)
-            if kind == "bm25":
-                want = c_oracle.bm25_scores(qtf, dat2, ind2, indptr, dl, idf, 1.2, 0.75, avgdl)
-            else:
-                want = c_oracle.tfidf_scores(qtf, dat2, ind2, indptr, idf)
-            assert np.array_equal(_bits(out[True][0][q]), _bits(want)), q
-            wi, wv = c_oracle.topk(want, k)
-            assert np.array_equal(out[True][1][q], wi) and np.array_equal(_bits(out[True][2][q]), _bits(np.where(wv == 0, np.float32(0), wv)))
-
-
-def test_slab_path_is_bypassed_for_non_finite_weights(b2r):
-    """An infinite query weight makes (idf * 0) * q a NaN for documents WITHOUT a posting: such a term must take the
-    posting path (the reference never touches those documents).  Scores against the oracle, inf and NaN included."""
-    from b200ret import synthetic as S
-    n_docs, n_vocab = 40_000, 3000
-    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 60, seed=61)
-    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
-    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl, tile_docs=2048)
-    assert ix.n_slabs > 0
-    q_ptr = np.array([0, 2, 4], np.int32)
-    q_terms = np.array([1, 700, 0, 3], np.int32)
-    q_w = np.array([np.inf, 1.0, 2.0, np.inf], np.float32)
-    s = ix.score_dense(q_ptr, q_terms, q_w).cpu().numpy()
-    for q in range(2):
-        qtf = np.zeros(n_vocab, np.float32)
-        qtf[q_terms[q_ptr[q]:q_ptr[q + 1]]] = q_w[q_ptr[q]:q_ptr[q + 1]]
-        want = c_oracle.bm25_scores(qtf, data, indices, indptr, dl, idf, 1.2, 0.75, avgdl)
-        assert np.array_equal(_bits(s[q]), _bits(want)), q
-    assert np.isinf(s).any() and np.isfinite(s).any()
