@@ -171,6 +171,9 @@ int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q
 /* Test / profiling hook: 0 makes b2r_search_batch use the plain "score everything, then select" path
  * instead of the fused-selection path (both are exact). */
 void b2r_set_fused_selection(int enabled);
+/* Test hook: candidate-list capacity of the fused path (0 = the plan's own choice).  A tiny capacity makes every
+ * list overflow, which routes every query through the exhaustive fallback (results are identical). */
+void b2r_set_fused_cap(int cap);
 /* Test / profiling hook: 0 = later index builds keep dense segments doc-ascending (no bank schedule). */
 void b2r_set_bank_schedule(int enabled);
 

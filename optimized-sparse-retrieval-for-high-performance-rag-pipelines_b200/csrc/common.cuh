@@ -110,12 +110,15 @@ size_t topk_keys_ws_bytes(int64_t n_rows, int64_t n, int32_t k);  // for topk_ke
 // 2^-20 relative so that it stays a valid bound for the exact scores (INT8 scan).
 // positive_floor = true: a threshold score <= 0 is replaced by "strictly positive scores only" (the caller must
 // then gate on short lists: topk_of_lists(min_cnt = k)).
+// zero_a / zero_b (optional): int32[n_rows] counters the kernel resets to 0 for its row.
 int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
-                  bool positive_floor, uint64_t *thr_out, cudaStream_t st);
+                  bool positive_floor, uint64_t *thr_out, cudaStream_t st, int32_t *zero_a = nullptr,
+                  int32_t *zero_b = nullptr);
 // keys_out[row, 0..k) = the k best of the first min(cnt[row], cap) keys of lists[row, 0..cap) (0-padded); cap <= 4096.
 // Rows with cnt[row] < min_cnt get cnt[row] = cap + 1, i.e. they are marked like overflowed rows for the fallback gate.
+// idx_out / val_out (optional): the decoded form of the ranked keys (-1 / -inf for "no candidate"); keys_out may be null.
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
-                  uint64_t *keys_out, cudaStream_t st);
+                  uint64_t *keys_out, cudaStream_t st, int64_t *idx_out = nullptr, float *val_out = nullptr);
 int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
                 int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st);
 

@@ -15,9 +15,10 @@
 // of those group maxima is a lower bound T of the k-th best score of the whole shard (k groups, hence k
 // documents, reach it).  (2) ALL tiles are scored with the FUSED epilogue, which appends the few documents
 // whose key beats T to a per-query candidate list; the exact top-k is the top-k of that list.  A query whose
-// list overflows is rescored exhaustively by the gated DENSE + top-k kernels that follow (they exit at once
-// for every other query), so the result is exact for any corpus order; the gate is evaluated on the device,
-// nothing synchronises.
+// list overflows (or comes up short) is rescored by the EXHAUSTIVE launch that follows: its CTAs leave at once for
+// every other query, and for a marked query they score every tile again and keep a streaming top-k in shared
+// memory (no score vector), so the result is exact for any corpus order with a workspace that does not grow with
+// the corpus; the gate is evaluated on the device, nothing synchronises.
 #include "common.cuh"
 
 #include <math.h>
@@ -141,7 +142,10 @@ __device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end
 // only synchronisation is __syncwarp: no CTA barrier, no atomics, no load imbalance between warps
 // (a dense term's postings are split by sub-tile through dense_ptr; a sparse term's small block is
 // scanned by every warp, each keeping the postings that fall in its range).
-enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1, SC_OUT_MAXIMA = 2 };
+enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1, SC_OUT_MAXIMA = 2, SC_OUT_EXHAUSTIVE = 3 };
+constexpr int SC_XK_CAP = 8192;    // EXHAUSTIVE: keys a CTA keeps in shared memory (k best so far + pending candidates)
+constexpr int SC_XK_CHUNK = 4096;  // EXHAUSTIVE: documents examined between two capacity checks
+constexpr int SC_X_PARTS = 8;      // EXHAUSTIVE: CTAs per query, each with its own share of the doc tiles
 enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1 };
 constexpr int SC_GROUPS_PER_TILE = 32 * B2R_SUBTILES;  // MAXIMA: one group maximum per lane
 
@@ -159,6 +163,13 @@ struct ScoreOut {
     int32_t cap;
     uint32_t n_docs;        // documents in this shard (tail of the last tile is padding)
     uint32_t doc_id_base;
+    // EXHAUSTIVE (runs for queries with gate[q] > gate_cap): exact top-k with no score vector
+    int32_t k;
+    uint64_t *x_parts;      // [queries, SC_X_PARTS, k] the k best of every part's tiles
+    int32_t *x_done;        // [queries] parts finished (zeroed by the caller); the last one merges
+    uint64_t *keys_final;   // [queries, k] (any of the three may be null)
+    int64_t *idx_final;
+    float *val_final;
 };
 
 template <int KIND, int OUT>
@@ -178,7 +189,31 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ql = blockIdx.x;  // query index inside this launch's chunk
     const int q = q0 + ql;
-    if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[ql] <= o.gate_cap) return;
+    if ((OUT == SC_OUT_DENSE || OUT == SC_OUT_EXHAUSTIVE) && o.gate != nullptr && o.gate[ql] <= o.gate_cap) return;
+    // EXHAUSTIVE: the CTA's k best keys so far live sorted in xk[0, x_kept), pending candidates behind them
+    uint64_t *xk = reinterpret_cast<uint64_t *>(acc + tile_docs);
+    __shared__ int x_cnt, x_last;
+    __shared__ uint64_t x_thr;
+    auto x_compact = [&]() {   // all threads: sort, keep the k best, raise the threshold
+        const int n = x_cnt;
+        int P = 32;
+        while (P < n) P <<= 1;
+        for (int i = n + (int)threadIdx.x; i < P; i += SC_THREADS) xk[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc<SC_THREADS>(xk, P);
+        if (threadIdx.x == 0) {
+            x_cnt = n < o.k ? n : o.k;
+            x_thr = n >= o.k ? xk[o.k - 1] : 0ull;
+        }
+        __syncthreads();
+    };
+    if (OUT == SC_OUT_EXHAUSTIVE) {
+        if (threadIdx.x == 0) {
+            x_cnt = 0;
+            x_thr = 0ull;
+        }
+        __syncthreads();
+    }
     const int sub = tile_docs / B2R_SUBTILES;
     double *acc_w = acc + w * sub;
     const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
@@ -294,6 +329,29 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             if (doc + 1 < o.n_docs) m = fmax(m, a.y);
         }
         o.scores[(int64_t)ql * o.scores_stride + (int64_t)y * SC_GROUPS_PER_TILE + w * 32 + lane] = __double2float_rn(m);
+    } else if (OUT == SC_OUT_EXHAUSTIVE) {
+        // every document whose key beats the k-th best so far becomes a pending candidate; the doc tile is examined
+        // in chunks that always fit behind the keys already held (x_cnt <= SC_XK_CAP - chunk before each chunk)
+        const int chunk = tile_docs < SC_XK_CHUNK ? tile_docs : SC_XK_CHUNK;
+        for (int c0 = 0; c0 < tile_docs; c0 += chunk) {
+            if (w * sub >= c0 && w * sub < c0 + chunk) {
+                const uint64_t thr = x_thr;
+                for (int i = lane * 2; i < sub; i += 64) {
+                    const double2 a = *reinterpret_cast<const double2 *>(acc_w + i);
+                    const double av[2] = {a.x, a.y};
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t doc = my_doc0 + i + c;
+                        if (doc < o.n_docs) {
+                            const uint64_t key = make_key(ord_f32(__double2float_rn(av[c])), o.doc_id_base + doc);
+                            if (key > thr) xk[atomicAdd(&x_cnt, 1)] = key;
+                        }
+                    }
+                }
+            }
+            // (one barrier: the last thread to arrive sees every append of the chunk, and x_cnt only grows)
+            if (__syncthreads_or(x_cnt > SC_XK_CAP - chunk)) x_compact();
+        }
     } else {
         const uint64_t thr = o.thr_keys[ql];
         const uint32_t thr_hi = (uint32_t)(thr >> 32);
@@ -332,6 +390,33 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
   }  // tile loop
+    if (OUT == SC_OUT_EXHAUSTIVE) {
+        // this part's k best -> x_parts; the last part of the query to finish merges all of them
+        __syncthreads();
+        x_compact();
+        const int k = o.k;
+        uint64_t *mine = o.x_parts + ((int64_t)ql * gridDim.y + blockIdx.y) * k;
+        for (int i = threadIdx.x; i < k; i += SC_THREADS) mine[i] = i < x_cnt ? xk[i] : 0ull;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) x_last = atomicAdd(o.x_done + ql, 1) == (int)gridDim.y - 1;
+        __syncthreads();
+        if (!x_last) return;
+        __threadfence();
+        const int n = (int)gridDim.y * k;   // <= SC_X_PARTS * 128 keys
+        const uint64_t *all = o.x_parts + (int64_t)ql * gridDim.y * k;
+        for (int i = threadIdx.x; i < n; i += SC_THREADS) xk[i] = __ldcg(all + i);
+        if (threadIdx.x == 0) x_cnt = n;
+        __syncthreads();
+        x_compact();
+        for (int i = threadIdx.x; i < k; i += SC_THREADS) {
+            const uint64_t key = xk[i];   // (0 beyond the number of documents: sorted last)
+            const int64_t at = (int64_t)ql * k + i;
+            if (o.keys_final) o.keys_final[at] = key;
+            if (o.idx_final) o.idx_final[at] = key ? (int64_t)(0xFFFFFFFFu - (uint32_t)key) : -1;
+            if (o.val_final) o.val_final[at] = key ? unord_f32((uint32_t)(key >> 32)) : __int_as_float(0xff800000);
+        }
+    }
 }
 
 struct ScoreLaunch {
@@ -353,12 +438,13 @@ template <int OUT>
 static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int tile_step, int n_y, const ScoreOut &o) {
     if (nq == 0 || n_y == 0) return B2R_OK;
     const b2r_index *ix = L.ix;
-    const size_t smem = (size_t)ix->tile_docs * sizeof(double);
+    const size_t smem = (size_t)ix->tile_docs * sizeof(double) + (OUT == SC_OUT_EXHAUSTIVE ? (size_t)SC_XK_CAP * 8 : 0);
     // a gated launch is expected to do nothing: keep its grid tiny (each CTA walks n_y / 4 tiles if it runs)
     // tiles per CTA: enough CTAs must remain to fill the GPU a few times over (148 SMs x 6 CTAs)
     int per_cta = g_tiles_per_cta;
     while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 6 * 4) per_cta >>= 1;
-    const int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
+    int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
+    if (OUT == SC_OUT_EXHAUSTIVE) grid_y = n_y < SC_X_PARTS ? n_y : SC_X_PARTS;
     dim3 grid((unsigned)nq, (unsigned)grid_y);
     if (ix->kind == B2R_KIND_BM25) {
         auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;
@@ -395,6 +481,7 @@ constexpr int FUSED_MIN_TILES = 8;    // below this the plain score + select pat
 constexpr int FUSED_MAX_K = 128;
 
 static bool g_fused_enabled = true;
+static int g_fused_cap = 0;
 // optional CUDA-event bracket around the fused scoring launch (bench.py's roofline of the dominant kernel)
 static bool g_profile = false;
 static cudaEvent_t g_ev[2] = {nullptr, nullptr};
@@ -420,6 +507,10 @@ static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
         p.cap = 256;
         while (p.cap < want && p.cap < 4096) p.cap <<= 1;
     }
+    if (g_fused_cap > 0) {   // b2r_set_fused_cap: test hook (tiny lists force the exhaustive fallback)
+        p.cap = g_fused_cap < k ? k : g_fused_cap;
+        if (p.cap > 4096) p.cap = 4096;
+    }
     p.n_groups = (int64_t)p.n_sample * SC_GROUPS_PER_TILE;
     // tile 0 is full (n_tiles >= 8) and holds min(tile_docs / 2, 256) non-empty groups
     const int groups_tile0 = ix->tile_docs / 2 < SC_GROUPS_PER_TILE ? ix->tile_docs / 2 : SC_GROUPS_PER_TILE;
@@ -427,12 +518,14 @@ static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
     return p;
 }
 
-// workspace bytes needed to run `qc` queries in one pass
+// workspace bytes needed to run `qc` queries in one pass.  The fused path never holds a score vector: group maxima
+// of the sample, thresholds, candidate lists, and the part lists of the exhaustive fallback -- C3 (8.8M docs, top-100,
+// 1024 queries): 0.2 GB.  Only the plain path (small shards, k > 128) keeps qc score rows.
 static size_t pass_bytes(const b2r_index *ix, const FusedPlan &fp, int64_t qc, int k) {
-    const size_t full = align_up((size_t)padded_docs(ix) * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k);
-    if (!fp.on) return full;
-    return full + align_up((size_t)fp.n_groups * 4 * (size_t)qc, 256) + align_up((size_t)qc * 8, 256) +
-           align_up((size_t)qc * fp.cap * 8, 256) + align_up((size_t)qc * 4, 256) + 256;
+    if (!fp.on) return align_up((size_t)padded_docs(ix) * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k);
+    return align_up((size_t)fp.n_groups * 4 * (size_t)qc, 256) + align_up((size_t)qc * 8, 256) +
+           align_up((size_t)qc * fp.cap * 8, 256) + 2 * align_up((size_t)qc * 4, 256) +
+           align_up((size_t)qc * SC_X_PARTS * k * 8, 256) + 256;
 }
 
 }  // namespace b2r
@@ -441,6 +534,8 @@ using namespace b2r;
 
 // test / profiling hook: 0 disables the fused-selection path (plain score + select is used)
 extern "C" void b2r_set_fused_selection(int enabled) { b2r::g_fused_enabled = enabled != 0; }
+// test hook: candidate-list capacity of the fused path (0 = the plan's own); a tiny value makes every list overflow
+extern "C" void b2r_set_fused_cap(int cap) { b2r::g_fused_cap = cap > 0 ? cap : 0; }
 
 extern "C" int b2r_set_profiling(int enabled) {
     if (enabled && !g_ev[0]) {
@@ -548,35 +643,39 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
                   pass_bytes(ix, fp, 1, k));
         return B2R_ERR_WORKSPACE;
     }
-    float *full = static_cast<float *>(carve((size_t)pad * 4 * (size_t)qc));
-    const size_t tk_full_bytes = topk_ws_bytes(qc, ix->n_docs, k);
-    void *tk_full = carve(tk_full_bytes);
-    float *maxima = nullptr;
-    uint64_t *thr = nullptr, *cand = nullptr;
-    int32_t *cand_cnt = nullptr;
+    float *full = nullptr, *maxima = nullptr;
+    void *tk_full = nullptr;
+    size_t tk_full_bytes = 0;
+    uint64_t *thr = nullptr, *cand = nullptr, *x_parts = nullptr;
+    int32_t *cand_cnt = nullptr, *x_done = nullptr;
     if (fp.on) {
         maxima = static_cast<float *>(carve((size_t)fp.n_groups * 4 * (size_t)qc));
         thr = static_cast<uint64_t *>(carve((size_t)qc * 8));
         cand = static_cast<uint64_t *>(carve((size_t)qc * fp.cap * 8));
         cand_cnt = static_cast<int32_t *>(carve((size_t)qc * 4));
+        x_done = static_cast<int32_t *>(carve((size_t)qc * 4));
+        x_parts = static_cast<uint64_t *>(carve((size_t)qc * SC_X_PARTS * k * 8));
+    } else {
+        full = static_cast<float *>(carve((size_t)pad * 4 * (size_t)qc));
+        tk_full_bytes = topk_ws_bytes(qc, ix->n_docs, k);
+        tk_full = carve(tk_full_bytes);
     }
 
     for (int64_t q0 = 0; q0 < n_queries; q0 += qc) {
         const int nq = (int)((n_queries - q0) < qc ? (n_queries - q0) : qc);
         uint64_t *kout = keys + q0 * k;
-        TopkOpts gate;
         if (fp.on) {
-            // 1. threshold: group maxima of every step-th tile, then the k-th largest of them per query
+            // 1. threshold: group maxima of every step-th tile, then the k-th largest of them per query (the same
+            //    kernel resets the query's candidate and fallback counters)
             ScoreOut so = {};
             so.scores = maxima;
             so.scores_stride = fp.n_groups;
             so.n_docs = (uint32_t)ix->n_docs;
             rc = launch_score<SC_OUT_MAXIMA>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
             if (rc) return rc;
-            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, true, thr, st);
+            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, true, thr, st, cand_cnt, x_done);
             if (rc) return rc;
             // 2. every tile: score, keep only the documents that reach the threshold
-            B2R_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * 4, st));
             ScoreOut fo = {};
             fo.thr_keys = thr;
             fo.cand = cand;
@@ -588,23 +687,37 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             rc = launch_score<SC_OUT_FUSED>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, fo);
             if (rc) return rc;
             if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[1], st));
-            // 3. exact top-k of the candidates
-            rc = topk_of_lists(cand, nq, fp.cap, cand_cnt, k, k, kout, st);
+            // 3. exact top-k of the candidates, ranked keys and their decoded form in one launch; a list that
+            //    overflowed or came up short marks its query (cand_cnt > cap)
+            rc = topk_of_lists(cand, nq, fp.cap, cand_cnt, k, k, kout, st, idx_out ? idx_out + q0 * k : nullptr,
+                               val_out ? val_out + q0 * k : nullptr);
             if (rc) return rc;
-            // 4. exact fallback, gated on the device to the queries whose list overflowed
-            gate.gate = cand_cnt;
-            gate.gate_cap = fp.cap;
+            // 4. exact fallback for the marked queries only (every other CTA leaves at once): exhaustive scoring with
+            //    a streaming top-k in shared memory -- no score vector, no workspace that grows with the corpus
+            ScoreOut xo = {};
+            xo.gate = cand_cnt;
+            xo.gate_cap = fp.cap;
+            xo.n_docs = (uint32_t)ix->n_docs;
+            xo.doc_id_base = (uint32_t)ix->doc_id_base;
+            xo.k = k;
+            xo.x_parts = x_parts;
+            xo.x_done = x_done;
+            xo.keys_final = kout;
+            xo.idx_final = idx_out ? idx_out + q0 * k : nullptr;
+            xo.val_final = val_out ? val_out + q0 * k : nullptr;
+            rc = launch_score<SC_OUT_EXHAUSTIVE>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, xo);
+            if (rc) return rc;
+            continue;
         }
         ScoreOut o = {};
         o.scores = full;
         o.scores_stride = pad;
-        o.gate = gate.gate;
-        o.gate_cap = gate.gate_cap;
         rc = launch_score<SC_OUT_DENSE>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, o);
         if (rc) return rc;
-        rc = topk_scores_rows(full, nq, ix->n_docs, pad, k, ix->doc_id_base, kout, tk_full, tk_full_bytes, st, gate);
+        rc = topk_scores_rows(full, nq, ix->n_docs, pad, k, ix->doc_id_base, kout, tk_full, tk_full_bytes, st);
         if (rc) return rc;
     }
+    if (fp.on) return B2R_OK;   // (decoded by the selection kernels)
     return decode_keys(keys, (int64_t)n_queries * k, idx_out, val_out, nullptr, 0, k, 0, st);
 }
 

@@ -351,7 +351,7 @@ constexpr int TL_MAX = 4096;  // longest list (32 KB of shared memory)
 
 __global__ void __launch_bounds__(TL_THREADS)
 topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__restrict__ cnt, int k, int min_cnt,
-                     uint64_t *__restrict__ out) {
+                     uint64_t *__restrict__ out, int64_t *__restrict__ idx_out, float *__restrict__ val_out) {
     __shared__ uint64_t arr[TL_MAX];
     __shared__ uint64_t best[B2R_TOPK_MAX_FAST];
     __shared__ uint32_t hist[256], wsum[8], s_bin, s_kk, s_n;
@@ -401,15 +401,21 @@ topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__res
     for (int i = n + tid; i < P; i += TL_THREADS) sortbuf[i] = 0ull;
     __syncthreads();
     bitonic_sort_desc<TL_THREADS>(sortbuf, P);
-    for (int i = tid; i < k; i += TL_THREADS) out[(int64_t)row * k + i] = sortbuf[i];
+    for (int i = tid; i < k; i += TL_THREADS) {   // ranked keys, and their decoded form when asked for
+        const uint64_t key = sortbuf[i];
+        const int64_t at = (int64_t)row * k + i;
+        if (out) out[at] = key;
+        if (idx_out) idx_out[at] = key ? (int64_t)(0xFFFFFFFFu - (uint32_t)key) : -1;
+        if (val_out) val_out[at] = key ? unord_f32((uint32_t)(key >> 32)) : __int_as_float(0xff800000);
+    }
 }
 
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
-                  uint64_t *keys_out, cudaStream_t st) {
+                  uint64_t *keys_out, cudaStream_t st, int64_t *idx_out, float *val_out) {
     if (n_rows == 0) return B2R_OK;
     B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap && k <= B2R_TOPK_MAX_FAST,
                   "top-k of lists: cap=%d / k=%d unsupported", cap, k);
-    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, 0, st>>>(lists, cap, cnt, k, min_cnt, keys_out);
+    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, 0, st>>>(lists, cap, cnt, k, min_cnt, keys_out, idx_out, val_out);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
@@ -419,7 +425,8 @@ int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, 
 // row's group maxima.  The rows are short (hundreds to a few ten thousand values) and stay in L1/L2.
 __global__ void __launch_bounds__(256)
 kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t row_stride, int k, int lower,
-                     int positive_floor, uint64_t *__restrict__ thr_out) {
+                     int positive_floor, uint64_t *__restrict__ thr_out, int32_t *__restrict__ zero_a,
+                     int32_t *__restrict__ zero_b) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t wsum[8];
     __shared__ uint32_t s_prefix, s_k, s_bin;
@@ -460,14 +467,17 @@ kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t
         // of them is caught by the short-list gate of topk_of_lists and rescored exhaustively.
         if (positive_floor && o <= 0x80000000u) thr = (0x80000000ull << 32) | 0xFFFFFFFFull;
         thr_out[blockIdx.x] = thr;
+        // the row's candidate counters start at zero (saves the caller a memset node per step)
+        if (zero_a) zero_a[blockIdx.x] = 0;
+        if (zero_b) zero_b[blockIdx.x] = 0;
     }
 }
 
 int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
-                  bool positive_floor, uint64_t *thr_out, cudaStream_t st) {
+                  bool positive_floor, uint64_t *thr_out, cudaStream_t st, int32_t *zero_a, int32_t *zero_b) {
     if (n_rows == 0) return B2R_OK;
     kth_of_maxima_kernel<<<(unsigned)n_rows, 256, 0, st>>>(maxima, n_groups, row_stride, k, lower ? 1 : 0,
-                                                           positive_floor ? 1 : 0, thr_out);
+                                                           positive_floor ? 1 : 0, thr_out, zero_a, zero_b);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }

@@ -25,7 +25,13 @@ import torch
 from . import _abi
 
 __all__ = ["TermMajorIndex", "pack_queries", "queries_from_dense", "reference_idf", "reference_avgdl",
-           "set_fused_selection"]
+           "set_fused_selection", "set_fused_cap"]
+
+
+def set_fused_cap(cap: int) -> None:
+    """Test hook: candidate-list capacity of the fused search path (0 = the library's own choice).  A tiny value
+    makes every list overflow and sends every query through the exhaustive fallback (results are identical)."""
+    _abi.lib.b2r_set_fused_cap(int(cap))
 
 
 def set_fused_selection(enabled: bool) -> None:

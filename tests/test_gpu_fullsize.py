@@ -136,7 +136,6 @@ def test_config3_8p8m_docs_top100_vs_oracle_and_sharded(b2r):
     torch.cuda.synchronize()
     ku = keys.cpu().numpy().view(np.uint64)
     assert bool((ku[:, :-1] > ku[:, 1:]).all())
-    del ix
     h_data, h_ind, h_ptr, h_dl = (t.cpu().numpy() for t in (data, ind, ptr, dl))
     c_oracle.use_all_host_threads()
     e = int(q_ptr[n_check])
@@ -144,7 +143,21 @@ def test_config3_8p8m_docs_top100_vs_oracle_and_sharded(b2r):
                                         idf, 1.2, 0.75, avgdl, k)
     assert np.array_equal(idx[:n_check].cpu().numpy(), wi)
     assert np.array_equal(_bits(val[:n_check].cpu().numpy()), _bits(_fold(wv)))
-    del h_data, h_ind, h_dl
+    # the workspace of the search does not grow with the corpus: all 1024 queries in ONE pass in well under 2 GB
+    # (a [Q, N] f32 score buffer would be 36 GB here), also when EVERY query overflows its candidate list and is
+    # rescored by the exhaustive fallback
+    import ctypes as C
+    mn, full = C.c_size_t(0), C.c_size_t(0)
+    b2r._abi.check(b2r._abi.lib.b2r_search_workspace(C.byref(ix._desc), nq, k, C.byref(mn), C.byref(full)))
+    assert full.value < 2 << 30 and ix._ws.numel() >= full.value
+    b2r.set_fused_cap(1)
+    try:
+        xi, xv = ix.search(q_ptr, q_terms, q_w, k)
+        torch.cuda.synchronize()
+    finally:
+        b2r.set_fused_cap(0)
+    assert torch.equal(xi, idx) and torch.equal(xv, val)
+    del h_data, h_ind, h_dl, ix
     for world in (2, 3):
         parts = []
         for r in range(world):

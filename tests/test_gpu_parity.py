@@ -512,6 +512,18 @@ def test_fused_selection_equals_plain_path_and_survives_overflow(b2r):
             pi, pv = ix.search(q_ptr, q_terms, q_w, k)
             b2r.set_fused_selection(True)
             assert torch.equal(fi, pi) and torch.equal(fv, pv), k
+            # every candidate list overflows (capacity = k): ALL queries take the exhaustive fallback (streaming
+            # top-k in shared memory, part lists merged by the last CTA of a query)
+            b2r.set_fused_cap(1)
+            try:
+                xi, xv, xk = ix.search(q_ptr, q_terms, q_w, k, return_keys=True)
+                hi_, hv_ = ix.search_host(q_ptr, q_terms, q_w, k)
+            finally:
+                b2r.set_fused_cap(0)
+            assert torch.equal(xi, pi) and torch.equal(xv, pv), k
+            assert np.array_equal(hi_, pi.cpu().numpy()) and np.array_equal(_bits(hv_), _bits(pv.cpu().numpy()))
+            ku = xk.cpu().numpy().view(np.uint64)
+            assert bool((ku[:, :-1] > ku[:, 1:]).all())
             wi, wv = _oracle_topk((d_, i_, p_, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, k)
             assert np.array_equal(fi.cpu().numpy(), wi), k
             assert np.array_equal(_bits(fv.cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv))), k
