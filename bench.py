@@ -395,6 +395,9 @@ def run_b200(args):
     G["graph"] = G["out"] = None
     idx = val = None
     fused_info = (t_step.value, cap.value)
+    exchange_kind = sharded.exchange
+    if world > 1 and sharded._peer is not None:
+        sharded._peer.check()          # raises if a wait inside the exchange kernel ever timed out
     sharded.ix = None
     sharded = ix = None
     torch.cuda.empty_cache()
@@ -435,7 +438,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
-            "run": {"sharding": f"doc-sharded x{world}", "tile_docs": args.tile_docs,
+            "run": {"sharding": f"doc-sharded x{world}", "exchange": exchange_kind, "tile_docs": args.tile_docs,
                     "postings_touched_per_step_rank0": postings, "cuda_graph_replay": graphed,
                     "launches_per_step": launches_per_step,
                     "selection": ("fused: threshold = k-th largest group maximum of every %dth tile, all tiles scored with "

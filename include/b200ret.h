@@ -208,6 +208,18 @@ int b2r_merge_candidates(const uint64_t *gathered, int32_t n_parts, int32_t n_qu
                          uint64_t *keys_out, int64_t *idx_out, float *val_out, void *workspace,
                          size_t workspace_bytes, void *stream);
 
+/* The same merge with the exchange built in, over peer memory (NVLink): every rank passes its ranked keys
+ * local_keys u64[n_queries, k] and the DEVICE array peer_bufs_dev[n_parts] of all ranks' receive buffers (memory every
+ * rank of the box can write, e.g. PyTorch symmetric memory; b2r_exchange_bytes(...) bytes each, zero-filled once and
+ * then owned by this call sequence).  One launch per rank: push my keys into every rank's buffer, wait chunk by chunk
+ * for the other ranks' keys, merge.  All ranks must make the same sequence of calls (same n_queries, k) on the same
+ * buffers; no host synchronisation and no NCCL call is involved, so the step can be captured in a CUDA graph.
+ * b2r_exchange_status synchronises and reports a timed-out wait (a rank that never called). */
+size_t b2r_exchange_bytes(int32_t n_parts, int32_t n_queries, int32_t k);
+int b2r_exchange_merge(const uint64_t *local_keys, void *const *peer_bufs_dev, int32_t rank, int32_t n_parts,
+                       int32_t n_queries, int32_t k, uint64_t *keys_out, int64_t *idx_out, float *val_out, void *stream);
+int b2r_exchange_status(const void *recv_buf, void *stream);
+
 /* Decode ranked keys into (global doc index, f32 score). */
 int b2r_decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, void *stream);
 

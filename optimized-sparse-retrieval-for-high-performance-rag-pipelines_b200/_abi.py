@@ -99,6 +99,9 @@ SIGNATURES = {
     "b2r_search_batch": (C.c_int, [_PIX, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "b2r_set_fused_selection": (None, [C.c_int]),
     "b2r_set_fused_cap": (None, [C.c_int]),
+    "b2r_exchange_bytes": (_SZ, [_I32, _I32, _I32]),
+    "b2r_exchange_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "b2r_exchange_status": (C.c_int, [_P, _P]),
     "b2r_set_bank_schedule": (None, [C.c_int]),
     "b2r_set_profiling": (C.c_int, [C.c_int]),
     "b2r_profile_fused_ms": (C.c_int, [C.POINTER(C.c_float), _P]),

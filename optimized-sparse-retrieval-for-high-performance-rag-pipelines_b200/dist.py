@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "global_statistics", "gather_candidates", "merge_shard_candidates", "sharded_int8_scan",
-           "ShardedBM25"]
+           "ShardedBM25", "PeerExchange"]
 
 
 def shard_range(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
@@ -63,12 +63,82 @@ def gather_candidates(local_keys: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+_PEER_CACHE: dict = {}
+
+
+class PeerExchange:
+    """Candidate exchange + merge in one kernel over peer memory (csrc/exchange.cu, b2r_exchange_merge).
+
+    Every rank allocates a receive buffer as PyTorch symmetric memory (CUDA VMM memory mapped into every process of
+    the group over NVLink) and hands the kernel the device array of all ranks' buffer addresses; from then on a step
+    is ONE launch per rank -- no NCCL call, no host synchronisation, capturable in a CUDA graph.  `create()` returns
+    None (and callers keep the NCCL all-gather path) when the allocation or the rendezvous fails, or
+    B2R_EXCHANGE=nccl is set."""
+
+    def __init__(self, n_queries: int, k: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _abi
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_queries, self.k = int(n_queries), int(k)
+        nbytes = int(_abi.lib.b2r_exchange_bytes(self.world, self.n_queries, self.k))
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        self.handle.barrier()          # every rank's buffer is zeroed before anyone pushes into it
+
+    @staticmethod
+    def create(n_queries: int, k: int, device, group=None) -> Optional["PeerExchange"]:
+        import os
+        if os.environ.get("B2R_EXCHANGE", "peer") == "nccl" or not dist.is_initialized():
+            return None
+        try:
+            return PeerExchange(n_queries, k, device, group)
+        except Exception as ex:      # no symmetric memory on this box / build: the NCCL path stays
+            import warnings
+            warnings.warn(f"b200ret: peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL all-gather")
+            return None
+
+    def fits(self, n_queries: int, k: int) -> bool:
+        return int(n_queries) == self.n_queries and int(k) == self.k
+
+    def merge(self, local_keys: torch.Tensor):
+        """local_keys i64[Q, k] (u64 payload) -> (idx i64[Q, k] global doc indices, val f32[Q, k]) of the union."""
+        from . import _abi
+        from .index import _stream_ptr
+        nq, k = int(local_keys.shape[0]), int(local_keys.shape[1])
+        assert self.fits(nq, k), "PeerExchange was sized for another (n_queries, k)"
+        dev = local_keys.device
+        idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        _abi.check(_abi.lib.b2r_exchange_merge(local_keys.contiguous().data_ptr(), self.peer_ptrs.data_ptr(), self.rank,
+                                               self.world, nq, k, None, idx.data_ptr(), val.data_ptr(), _stream_ptr(dev)),
+                   "exchange + merge")
+        return idx, val
+
+    def check(self) -> None:
+        """Synchronise and raise if a wait inside the kernel ever timed out."""
+        from . import _abi
+        from .index import _stream_ptr
+        _abi.check(_abi.lib.b2r_exchange_status(self.buf.data_ptr(), _stream_ptr(self.buf.device)), "exchange status")
+
+
 def merge_shard_candidates(local_keys: torch.Tensor, k: int, group=None):
     """all-gather the ranked [Q, k] candidate keys of every shard and merge them on the GPU
     (b2r_merge_candidates).  Returns (idx i64[Q,k] global doc indices, val f32[Q,k])."""
     from . import _abi
     from .index import _stream_ptr
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1 and local_keys.is_cuda:      # peer-memory exchange when available (cached per batch shape)
+        ck = (int(local_keys.shape[0]), int(k), str(local_keys.device), id(group))
+        if ck not in _PEER_CACHE:
+            _PEER_CACHE[ck] = PeerExchange.create(ck[0], ck[1], local_keys.device, group)
+        if _PEER_CACHE[ck] is not None:
+            return _PEER_CACHE[ck].merge(local_keys)
     gathered = gather_candidates(local_keys, group)
     nq = int(local_keys.shape[0])
     dev = local_keys.device
@@ -98,6 +168,9 @@ class ShardedBM25:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._ws = None
+        self._peer: Optional[PeerExchange] = None
+        self._peer_tried = False
+        self.exchange = "none" if self.world == 1 else "nccl all_gather + merge kernel"
 
     def search(self, q_ptr, q_terms, q_weights, k: int):
         from . import _abi
@@ -105,6 +178,16 @@ class ShardedBM25:
         _idx, _val, keys = self.ix.search(q_ptr, q_terms, q_weights, k, return_keys=True)
         if self.world == 1:
             return _idx, _val
+        # candidate exchange: one fused kernel over peer memory when the box offers it (sized on first use: every
+        # rank runs the same batches), else NCCL all-gather + merge kernel
+        if keys.is_cuda and (self._peer is None or not self._peer.fits(keys.shape[0], k)) and not (
+                self._peer_tried and self._peer is None):
+            self._peer = PeerExchange.create(int(keys.shape[0]), int(k), keys.device, self.group)
+            self._peer_tried = True
+            if self._peer is not None:
+                self.exchange = "peer-memory exchange+merge kernel (symmetric memory over NVLink)"
+        if self._peer is not None and self._peer.fits(keys.shape[0], k):
+            return self._peer.merge(keys)
         gathered = gather_candidates(keys, self.group)
         nq = int(keys.shape[0])
         dev = keys.device

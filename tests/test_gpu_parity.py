@@ -773,3 +773,57 @@ def test_full_size_1m_docs_properties(b2r):
                                                      ws.data_ptr(), ws.numel(),
                                                      int(torch.cuda.current_stream().cuda_stream)))
     assert torch.equal(mi, idx) and torch.equal(mv, val)
+
+
+# ----------------------------------------------------------------------------------- peer-memory exchange + merge
+@pytest.mark.parametrize("world,nq,k", [(3, 300, 10), (2, 1024, 100), (4, 7, 1)])
+def test_exchange_merge_kernel_emulated_ranks_on_one_gpu(b2r, world, nq, k):
+    """b2r_exchange_merge (one launch per rank: push my ranked keys into every rank's receive buffer, wait chunk by
+    chunk, merge by rank counting).  The ranks are emulated on ONE GPU: `world` receive buffers in plain device
+    memory, one stream per rank so that the kernels run side by side and can wait for each other; repeated calls
+    exercise the epoch / parity double buffering.  Expected = top-k of the union of the ranks' lists."""
+    lib = b2r._abi.lib
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(100 + world)
+    nbytes = int(lib.b2r_exchange_bytes(world, nq, k))
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    ptrs = torch.tensor([b_.data_ptr() for b_ in bufs], dtype=torch.int64, device=dev)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for rep in range(4):
+        # distinct keys (score bits << 32 | ~doc); every rank's list ranked descending, some lists short (0-padded)
+        lists = np.zeros((world, nq, k), np.uint64)
+        for r in range(world):
+            sc = rng.integers(1, 1 << 20, (nq, k)).astype(np.uint64)
+            doc = (rng.permutation(nq * k).reshape(nq, k) + r * nq * k).astype(np.uint64)
+            key = (sc << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - doc)
+            key = -np.sort(-key.astype(np.int64), axis=1)
+            key = key.astype(np.uint64)
+            short = rng.random(nq) < 0.2
+            cut = rng.integers(0, k + 1, nq)
+            for q in np.nonzero(short)[0]:
+                key[q, cut[q]:] = 0
+            lists[r] = key
+        local = [torch.from_numpy(lists[r].view(np.int64)).to(dev) for r in range(world)]
+        outs = []
+        torch.cuda.synchronize()
+        for r in range(world):
+            ko = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            io = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            vo = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            with torch.cuda.stream(streams[r]):
+                b2r._abi.check(lib.b2r_exchange_merge(local[r].data_ptr(), ptrs.data_ptr(), r, world, nq, k, ko.data_ptr(),
+                                                      io.data_ptr(), vo.data_ptr(), int(streams[r].cuda_stream)))
+            outs.append((ko, io, vo))
+        torch.cuda.synchronize()
+        for r in range(world):
+            b2r._abi.check(lib.b2r_exchange_status(bufs[r].data_ptr(), None), f"rank {r}")
+        union = np.concatenate([lists[r] for r in range(world)], axis=1)
+        want = -np.sort(-union.view(np.int64), axis=1)[:, :k]
+        want_u = want.view(np.uint64)
+        for r in range(world):
+            ko, io, vo = (x.cpu().numpy() for x in outs[r])
+            assert np.array_equal(ko.view(np.uint64), want_u), (rep, r)
+            wi = np.where(want_u != 0, (np.uint64(0xFFFFFFFF) - (want_u & np.uint64(0xFFFFFFFF))).astype(np.int64), -1)
+            assert np.array_equal(io, wi), (rep, r)
+            assert np.all(np.isneginf(vo[want_u == 0]))
