@@ -444,7 +444,9 @@ static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int
     int per_cta = g_tiles_per_cta;
     while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 6 * 4) per_cta >>= 1;
     int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
-    if (OUT == SC_OUT_EXHAUSTIVE) grid_y = n_y < SC_X_PARTS ? n_y : SC_X_PARTS;
+    // EXHAUSTIVE: normally every CTA leaves at once, so the grid is kept small on small shards (a marked query is then
+    // walked by fewer, longer-running CTAs: one part per 32 doc tiles, at most SC_X_PARTS)
+    if (OUT == SC_OUT_EXHAUSTIVE) grid_y = n_y / 32 < 1 ? 1 : (n_y / 32 > SC_X_PARTS ? SC_X_PARTS : n_y / 32);
     dim3 grid((unsigned)nq, (unsigned)grid_y);
     if (ix->kind == B2R_KIND_BM25) {
         auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;
