@@ -46,6 +46,8 @@ WORKLOADS = {
     "small": (100_000, 20_000, 60.0, 256, 10, "small smoke workload (not a bench line)"),
     "c2s8": (125_000, 100_000, 60.0, 1024, 10,
              "one rank's share of c2 at 8 GPUs on a single GPU: fixed per-step overheads (not a bench line)"),
+    "c2s4": (250_000, 100_000, 60.0, 1024, 10, "one rank's share of c2 at 4 GPUs on a single GPU (profiling, not a bench line)"),
+    "c2s2": (500_000, 100_000, 60.0, 1024, 10, "one rank's share of c2 at 2 GPUs on a single GPU (profiling, not a bench line)"),
 }
 FALLBACK_HBM_GBS = 6650.0
 # queries of the batch the CPU arm times per step (the first n of the 1024; they are i.i.d. draws)
