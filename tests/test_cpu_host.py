@@ -234,3 +234,62 @@ def test_product_quantisers_match_the_reference_outputs(golden_dir):
     assert np.array_equal(q, z["d8"][:len(q)]) and np.array_equal(sc, z["dscale"][:len(q)])
     q2, s2 = S.quantize_queries(z["emb"][:4])
     assert q2.dtype == np.int8 and np.abs(q2).max() == 127 and np.allclose(q2 * s2[:, None], z["emb"][:4], atol=s2.max())
+
+
+# ----------------------------------------------------------------------------------- f2: the reference's own registry
+def _reference_root():
+    """Where the reference package can be imported from: the mounted checkout, or the files oracle/make_ref.py placed
+    under oracle/_ref (they travel to the GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for root in ("/root/reference", os.path.join(here, "oracle", "_ref")):
+        if os.path.isfile(os.path.join(root, "rag_system", "core", "retriever_registry.py")):
+            return root
+    return None
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="reference package not available (no /root/reference, no oracle/_ref)")
+def test_plugin_registers_into_the_reference_registry():
+    """The plugin goes into the REFERENCE's RetrieverRegistry (rag_system/core/retriever_registry.py:562-599), is
+    created by its create() with the config shape the reference uses, and has the constructor / method signatures of
+    the class it replaces (OptimizedBM25Retriever, :120-262).  No CUDA call happens before an index is built."""
+    import inspect
+    import sys
+    root = _reference_root()
+    sys.path.insert(0, root)
+    try:
+        import b200ret
+        from b200ret import retriever as plug
+        from rag_system.core import retriever_registry as rr
+        stock_create = rr.RetrieverRegistry.__dict__["create"]
+        try:
+            reg = plug.install()
+            assert reg is rr.RetrieverRegistry
+            assert "bm25_b200" in reg.list_available()["registered_custom"]
+            r = reg.create({"type": "bm25_b200", "params": {"k1": 0.9, "b": 0.4}})
+            assert isinstance(r, b200ret.B200BM25Retriever) and (r.k1, r.b) == (0.9, 0.4)
+            with pytest.raises(ValueError, match="Index not built"):
+                r.search({"q": "anything"}, top_k=5)
+            with pytest.raises(ValueError, match="Empty corpus"):
+                r.build_index_from_corpus({})
+            ref_cls = rr.OptimizedBM25Retriever
+            for name in ("__init__", "build_index_from_corpus", "search", "clear_cache"):
+                want = list(inspect.signature(getattr(ref_cls, name)).parameters)
+                got = list(inspect.signature(getattr(b200ret.B200BM25Retriever, name)).parameters)
+                assert got == want, (name, got, want)
+            # a maintainer's switch-over: the built-in names route to the plugin, everything else stays stock
+            plug.install(take_over_bm25=True)
+            t = reg.create({"type": "tfidf"})
+            assert isinstance(t, b200ret.B200BM25Retriever) and (t.k1, t.b) == (1000.0, 0.0)
+            assert isinstance(reg.create("bm25"), b200ret.B200BM25Retriever)
+            with pytest.raises(ValueError, match="Unknown retriever"):
+                reg.create({"type": "no_such_method"})
+            # the pipeline's constructor contract (evaluate_rag_pipeline.py:165-180)
+            p = b200ret.B200BM25Retriever.from_pipeline_config({"type": "bm25", "params": {"k1": 1.5, "top_k": 50}},
+                                                               {"cores": 8, "memory_gb": 64})
+            assert (p.k1, p.b, p.method) == (1.5, 0.75, "bm25")
+            assert p.cache_file_for({"d2": {}, "d1": {}}).name.startswith("bm25_index_")
+        finally:
+            rr.RetrieverRegistry.create = stock_create
+            rr.RetrieverRegistry._retrievers.pop("bm25_b200", None)
+    finally:
+        sys.path.remove(root)

@@ -719,6 +719,14 @@ def test_service_save_load_and_reference_cache_file(b2r, golden_dir, tmp_path):
     assert svc3.search_bm25(g["queries"], top_k=10) == want
 
 
+def _reference_root():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for root in ("/root/reference", os.path.join(here, "oracle", "_ref")):
+        if os.path.isfile(os.path.join(root, "rag_system", "core", "retriever_registry.py")):
+            return root
+    return None
+
+
 def test_registry_plugin_shape(b2r, golden_dir):
     with open(os.path.join(golden_dir, "service_text.json")) as f:
         g = json.load(f)
@@ -734,6 +742,68 @@ def test_registry_plugin_shape(b2r, golden_dir):
     r.build_index_from_corpus(g["corpus"])
     out = r.search({"a": g["queries"]["query_1"]}, top_k=10)
     assert sorted(out["a"].values(), reverse=True) == sorted(g["ref_top10"]["query_1"].values(), reverse=True)
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="reference package not available (no /root/reference, no oracle/_ref)")
+def test_plugin_in_the_reference_registry_vs_the_reference_retriever(b2r, tmp_path):
+    """f2 end to end: both retrievers come out of the REFERENCE's RetrieverRegistry.create -- its own
+    OptimizedBM25Retriever (Numba, CPU) and the registered B200 plugin -- are built on the same text corpus and
+    answer the same query set.  Same scores in the same order for every query (ids wherever scores are not tied).
+    Then the pipeline hook: prefetch() scores the whole query set in ONE GPU call and the pipeline-style loop of
+    <= 100-query search() calls that follows launches no kernel; and the reference's own index cache file
+    (evaluate_rag_pipeline.py:277-293) loads into the plugin."""
+    import sys
+    from b200ret import synthetic as S
+    root = _reference_root()
+    sys.path.insert(0, root)
+    try:
+        from b200ret import retriever as plug
+        from rag_system.core import retriever_registry as rr
+        reg = plug.install()
+        corpus = S.fiqa_shape_corpus(num_docs=6000, avg_doc_length=60, vocab_size=8000, seed=7)
+        queries = S.fiqa_shape_queries(num_queries=260, avg_query_length=6, vocab_size=8000, seed=8)
+        queries["blank"] = ""
+        queries["oov"] = "zzzz qqqq"
+        ref = reg.create({"type": "bm25", "params": {"k1": 1.4, "b": 0.6}})
+        mine = reg.create({"type": "bm25_b200", "params": {"k1": 1.4, "b": 0.6}})
+        assert type(ref).__name__ == "OptimizedBM25Retriever" and isinstance(mine, b2r.B200BM25Retriever)
+        ref.build_index_from_corpus(corpus)
+        mine.build_index_from_corpus(corpus)
+        assert mine.vocabulary == ref.vocabulary and mine.doc_ids == ref.doc_ids and mine.avgdl == ref.avgdl
+        assert np.array_equal(mine.idf_weights, ref.idf_weights)
+        want = ref.search(queries, top_k=20)
+        got = mine.search(queries, top_k=20)
+        assert list(got) == list(want)
+        n_nonempty = 0
+        for qid in queries:
+            wv, gv = list(want[qid].values()), list(got[qid].values())
+            assert gv == wv, qid
+            if len(set(wv)) == len(wv) and len(wv) < 20:       # no ties, and no tie at the cut either
+                assert list(got[qid]) == list(want[qid]), qid
+            n_nonempty += bool(wv)
+        assert n_nonempty > 200 and got["blank"] == {} and got["oov"] == {}
+        # the pipeline hook
+        mine.clear_cache()
+        lib = b2r._abi.lib
+        assert mine.prefetch({q: {"text": t} for q, t in queries.items()}, top_k=20) >= 250
+        n0 = lib.b2r_launch_count()
+        items = list(queries.items())
+        merged = {}
+        for i in range(0, len(items), 100):                    # evaluate_rag_pipeline.py:741-780
+            merged.update(mine.search(dict(items[i:i + 100]), top_k=20))
+        assert lib.b2r_launch_count() == n0 and merged == got
+        # a cache file with the reference's keys, object arrays included (what np.savez makes of its Python lists)
+        cache = tmp_path / "bm25_index_cafe.npz"
+        tf = ref.corpus_tf
+        np.savez_compressed(cache, tf_data=tf.data, tf_indices=tf.indices, tf_indptr=tf.indptr, tf_shape=tf.shape,
+                            doc_lengths=ref.doc_lengths, idf=ref.idf_weights, vocabulary=list(ref.vocabulary.keys()),
+                            doc_ids=ref.doc_ids, avgdl=ref.avgdl)
+        again = reg.create({"type": "bm25_b200", "params": {"k1": 1.4, "b": 0.6}})
+        again.load_cached_index(cache)
+        assert again.search(queries, top_k=20) == got
+        rr.RetrieverRegistry._retrievers.pop("bm25_b200", None)
+    finally:
+        sys.path.remove(root)
 
 
 # ----------------------------------------------------------------------------------- full size (C2) properties
