@@ -3,8 +3,10 @@
 The reference's RetrievalService opens a MemoryIndex file in its constructor
 (rag_system/core/retrieval.py:103; format in rag_system/core/memory_index.py:22-34, 159-195) and
 fetches result texts from it (retrieval.py:356-462).  Text blobs are NOT on the scoring path and
-the store itself is out of scope ("boundary only"); this module reads and
-writes the same on-disk layout so that an index file made by either side opens on the other:
+the store itself is out of scope (the fetch that FOLLOWS a search is); this
+module reads and writes the same on-disk layout so that an index file made by either side opens on
+the other, and serves the batched fetch behind get_documents / get_search_results: one pass over the
+mmap in file order, every distinct document read once, zlib inflation on a thread pool:
 
   file header  "QQI"  : num_docs u64, data_size u64, max_id_len u32
   per document "QQQB" : id_len, text_len, title_len, flags ; id ; text ; title ; u64 meta_len ; meta
@@ -152,8 +154,47 @@ class MemoryIndex:
         metadata = pickle.loads(zlib.decompress(meta) if flags & _Z_META else meta)
         return Document(id=doc_id, text=text, title=title, metadata=metadata)
 
+    def _raw(self, off: int):
+        """(flags, text bytes, title bytes, metadata bytes) of the record at `off`, still compressed."""
+        id_len, text_len, title_len, flags = _DOC_HDR.unpack_from(self._map, off)
+        p = off + _DOC_HDR.size + id_len
+        text = bytes(self._map[p:p + text_len])
+        p += text_len
+        title = bytes(self._map[p:p + title_len])
+        p += title_len
+        (meta_len,) = _U64.unpack_from(self._map, p)
+        return flags, text, title, bytes(self._map[p + 8:p + 8 + meta_len])
+
+    @staticmethod
+    def _decode(item) -> Document:
+        doc_id, (flags, text, title, meta) = item
+        text = (zlib.decompress(text) if flags & _Z_TEXT else text).decode("utf-8")
+        title = (zlib.decompress(title) if flags & _Z_TITLE else title).decode("utf-8")
+        metadata = pickle.loads(zlib.decompress(meta) if flags & _Z_META else meta)
+        return Document(id=doc_id, text=text, title=title, metadata=metadata)
+
     def get_documents(self, doc_ids: List[str], num_workers: int = 4) -> List[Optional[Document]]:
-        return [self.get_document(d) for d in doc_ids]
+        """memory_index.py:413-468, batched: the distinct ids of the call are looked up once, their records are read
+        in FILE ORDER (one forward pass over the mmap instead of one random access per id and per worker), and the
+        inflation runs on `num_workers` threads (zlib releases the GIL).  Result order = request order, None for an
+        unknown id."""
+        if self._map is None or not doc_ids:
+            return [None] * len(doc_ids)
+        wanted = {}
+        for d in doc_ids:
+            if d not in wanted:
+                off = self._where.get(d)
+                if off is not None:
+                    wanted[d] = off
+        raw = [(d, self._raw(off)) for d, off in sorted(wanted.items(), key=lambda kv: kv[1])]
+        if num_workers > 1 and len(raw) >= 64:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=num_workers) as pool:
+                docs = list(pool.map(self._decode, raw, chunksize=max(1, len(raw) // (4 * num_workers))))
+        else:
+            docs = [self._decode(r) for r in raw]
+        by_id = {doc.id: doc for doc in docs}
+        return [by_id.get(d) for d in doc_ids]
 
     def get_document_count(self) -> int:
         return len(self._where)

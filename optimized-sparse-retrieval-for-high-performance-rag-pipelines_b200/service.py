@@ -292,8 +292,9 @@ class RetrievalService:
                 out.append({"doc_id": self.doc_ids[int(i)], "score": float(s)})
         return out
 
-    # ------------------------------------------------------------------ document fetch (boundary only)
+    # ------------------------------------------------------------------ document fetch
     def get_document(self, doc_id: str) -> Optional[Document]:
+        """retrieval.py:356-365."""
         with self.cache_lock:
             if doc_id in self._cache:
                 return self._cache[doc_id]
@@ -303,9 +304,20 @@ class RetrievalService:
         return doc
 
     def get_documents(self, doc_ids: List[str]) -> List[Optional[Document]]:
-        return [self.get_document(d) for d in doc_ids]
+        """retrieval.py:367-400: cached documents are served from the cache, every other id of the call goes to the
+        store in ONE batched fetch (docstore.MemoryIndex.get_documents: file-order pass + threaded inflation); result
+        order = request order, None for an unknown id."""
+        with self.cache_lock:
+            have = {d: self._cache[d] for d in doc_ids if d in self._cache}
+        missing = [d for d in dict.fromkeys(doc_ids) if d not in have]
+        if missing:
+            fetched = self.index.get_documents(missing, num_workers=self.num_workers)
+            self._remember(fetched)
+            have.update({doc.id: doc for doc in fetched if doc})
+        return [have.get(d) for d in doc_ids]
 
     def _remember(self, docs) -> None:
+        """retrieval.py:438-446 (_cache_documents): bounded cache, oldest entry evicted first."""
         with self.cache_lock:
             for d in docs:
                 if d:
@@ -314,6 +326,7 @@ class RetrievalService:
                         self._cache.pop(next(iter(self._cache)))
 
     def get_search_results(self, query_results: List[Dict], include_text: bool = True) -> List[Dict]:
+        """retrieval.py:436-462: one batched fetch for all results of the call."""
         out = []
         for doc, r in zip(self.get_documents([r["doc_id"] for r in query_results]), query_results):
             if doc:
@@ -321,6 +334,25 @@ class RetrievalService:
                 if include_text:
                     d.update({"text": doc.text, "title": doc.title, "metadata": doc.metadata})
                 out.append(d)
+        return out
+
+    def fetch_results(self, results: Dict[str, Dict[str, float]], include_text: bool = True) -> Dict[str, List[Dict]]:
+        """The fetch that follows a batched search: search_bm25's {qid: {doc_id: score}} for a whole query set ->
+        {qid: [result dicts in rank order]} (the dict shape of get_search_results), with ONE store fetch for the union
+        of all result lists."""
+        ids = list(dict.fromkeys(d for r in results.values() for d in r))
+        docs = dict(zip(ids, self.get_documents(ids)))
+        out: Dict[str, List[Dict]] = {}
+        for qid, r in results.items():
+            rows = []
+            for d, s in r.items():
+                doc = docs.get(d)
+                if doc:
+                    row = {"id": doc.id, "score": s}
+                    if include_text:
+                        row.update({"text": doc.text, "title": doc.title, "metadata": doc.metadata})
+                    rows.append(row)
+            out[qid] = rows
         return out
 
     # ------------------------------------------------------------------ housekeeping

@@ -293,3 +293,37 @@ def test_plugin_registers_into_the_reference_registry():
             rr.RetrieverRegistry._retrievers.pop("bm25_b200", None)
     finally:
         sys.path.remove(root)
+
+
+# ----------------------------------------------------------------------------------- f4: batched document fetch
+def test_batched_document_fetch_matches_per_id_fetch(tmp_path):
+    """docstore.MemoryIndex.get_documents / RetrievalService.get_documents / get_search_results / fetch_results
+    (reference: rag_system/core/retrieval.py:356-462, memory_index.py:413-468): request order, duplicates, unknown
+    ids, compressed and uncompressed records, the threaded path (>= 64 documents) and the service-level cache."""
+    import b200ret
+    rng = np.random.default_rng(5)
+    path = tmp_path / "docs.idx"
+    store = b200ret.MemoryIndex(path, create=True)
+    docs = []
+    for i in range(300):
+        n = int(rng.integers(1, 400))                     # short texts stay raw, long ones are zlib-compressed
+        docs.append(b200ret.Document(id=f"d{i}", text=" ".join(f"w{int(x)}" for x in rng.integers(0, 50, n)),
+                                     title=f"title {i}" if i % 3 else "", metadata={"i": i} if i % 2 else {}))
+    store.add_documents(docs)
+    ids = [f"d{int(i)}" for i in rng.integers(0, 300, 500)] + ["nope", "d7", "d7"]
+    got = store.get_documents(ids, num_workers=4)
+    one_by_one = [store.get_document(d) for d in ids]
+    assert got == one_by_one and got[500] is None and got[501] == got[502] == docs[7]
+    assert store.get_documents(ids[:10], num_workers=1) == one_by_one[:10]
+    assert store.get_documents([]) == []
+    store.close()
+    with b200ret.RetrievalService(path, cache_size=50) as svc:
+        assert svc.get_documents(ids) == one_by_one          # more distinct documents than the cache holds
+        assert len(svc._cache) <= 50
+        res = [{"doc_id": "d3", "score": 2.5}, {"doc_id": "nope", "score": 1.0}, {"doc_id": "d4", "score": 0.5}]
+        rows = svc.get_search_results(res)
+        assert [r["id"] for r in rows] == ["d3", "d4"] and rows[0]["text"] == docs[3].text and rows[0]["score"] == 2.5
+        assert set(svc.get_search_results(res, include_text=False)[0]) == {"id", "score"}
+        batch = svc.fetch_results({"q1": {"d10": 3.0, "d11": 2.0}, "q2": {}, "q3": {"d11": 9.0, "zzz": 1.0}})
+        assert [r["id"] for r in batch["q1"]] == ["d10", "d11"] and batch["q2"] == [] and len(batch["q3"]) == 1
+        assert batch["q3"][0]["metadata"] == docs[11].metadata
