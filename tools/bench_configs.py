@@ -269,9 +269,29 @@ def run_int8_sharded(args):
     os._exit(0)
 
 
+def run_dense(args):
+    """a8: RetrievalService.search_by_vector's fp32 gemv + top-k (retrieval.py:402-436) on a resident embedding matrix:
+    b2r_f32_dot_topk at N x 768 f32, Q = 1 / 8 / 64 queries, top-10; bytes = the matrix once per pass of 8 queries."""
+    dev = torch.device("cuda")
+    n, dim, k = args.docs, 768, 10
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    emb = torch.randn((n, dim), device=dev, generator=g, dtype=torch.float32)
+    for nq in (1, 8, 64):
+        q = torch.randn((nq, dim), device=dev, generator=g, dtype=torch.float32)
+        ms = timed(lambda: b200ret.dense_topk(emb, q, k), steps=5, warmup=2)
+        passes = (nq + 7) // 8
+        rec = {"config": f"a8: fp32 {dim}-d gemv + top-{k}, {n} vectors resident in HBM", "queries": nq, "ms": ms,
+               "queries_per_s": nq / (ms * 1e-3), "matrix_gbs": passes * n * dim * 4 / (ms * 1e-3) / 1e9,
+               "frac_of_hbm_peak": passes * n * dim * 4 / (ms * 1e-3) / 1e9 / PEAK}
+        idx, val = b200ret.dense_topk(emb, q[:1], k)
+        want = torch.topk(emb @ q[0], k)
+        rec["top_ids_match_torch"] = bool(torch.equal(torch.sort(idx[0]).values, torch.sort(want.indices).values))
+        print(json.dumps(rec), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["int8", "c3", "c4"])
+    ap.add_argument("what", choices=["int8", "c3", "c4", "dense"])
     ap.add_argument("--docs", type=int, default=None)
     ap.add_argument("--queries", type=int, nargs="+", default=[1, 64, 1024])
     ap.add_argument("--check", type=int, default=1)
@@ -283,13 +303,15 @@ def main():
                     help="int8: sweep the thread-block cluster cap of the tcgen05 kernel (A/B measurement)")
     args = ap.parse_args()
     if args.docs is None:
-        args.docs = {"int8": 2_000_000, "c3": 8_800_000, "c4": 2_200_000}[args.what]
+        args.docs = {"int8": 2_000_000, "c3": 8_800_000, "c4": 2_200_000, "dense": 2_000_000}[args.what]
     if args.what == "c3" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_c3_sharded(args)
     elif args.what == "int8" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         run_int8_sharded(args)
     elif args.what == "int8":
         run_int8(args)
+    elif args.what == "dense":
+        run_dense(args)
     else:
         run_sparse(args, args.what)
 
