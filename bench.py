@@ -7,7 +7,9 @@ A step = one pass of the hot path (score 1024 queries against the corpus, select
 N > 1 exchange + merge the per-shard candidates).  The 1M-document corpus is doc-sharded over the
 N ranks (strong scaling: the corpus is fixed, as the metric names it).  Prints ONE JSON line.
 
-  value         queries/s with the index and the query batch resident in HBM (CUDA events, max over ranks)
+  value         queries/s with the index and the query batch resident in HBM (CUDA events, max over ranks); the K
+                steps run as K/2 replays of a captured graph that holds two independent batches on two streams
+                (run.batches_in_flight; run.ms_per_step_one_batch_in_flight is the serial figure)
   e2e           the same through the host-buffer C-ABI call (pinned host queries -> H2D -> score ->
                 select -> D2H of ids+scores inside the timed region)
   roofline      the scorer (score_tiles_kernel, fused-selection epilogue): algorithmic bytes per launch
