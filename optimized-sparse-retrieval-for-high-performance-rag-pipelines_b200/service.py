@@ -226,27 +226,32 @@ class RetrievalService:
                 pending[cache_key].append(qid)
                 continue
             counts = Counter(_WORD.findall(text.lower()))
-            terms = [(self.vocabulary[t], float(c)) for t, c in counts.items() if t in self.vocabulary]
+            voc = self.vocabulary
+            terms = sorted((voc[t], float(c)) for t, c in counts.items() if t in voc)   # unique ids, ascending
             if not terms:
                 results[qid] = {}
                 continue
             results[qid] = None
             pending[cache_key] = [qid]
             keys_in_order.append(cache_key)
-            packed.append((np.array([t for t, _ in terms]), np.array([c for _, c in terms], np.float32)))
+            packed.append(terms)
 
         if packed:
             ix = self._sync_gpu_index()
             n_docs = len(self.doc_ids)
             k = int(top_k)
+            # CSR-style packing of the batch (what pack_queries produces; the term lists are already unique, sorted and
+            # positive, so the flat arrays are built in one go)
+            q_ptr = np.zeros(len(packed) + 1, np.int32)
+            np.cumsum([len(t) for t in packed], out=q_ptr[1:])
+            q_terms = np.fromiter((t for q in packed for t, _ in q), np.int32, count=int(q_ptr[-1]))
+            q_w = np.fromiter((c for q in packed for _, c in q), np.float32, count=int(q_ptr[-1]))
             if k < 1:
-                top = [(np.zeros(0, np.int64), np.zeros(0, np.float32))] * len(packed)
+                top = [([], [])] * len(packed)
             elif k <= 1024:
-                q_ptr, q_terms, q_w = pack_queries(packed)
                 idx, val = ix.search_host(q_ptr, q_terms, q_w, min(k, n_docs))
-                top = [(idx[i], val[i]) for i in range(len(packed))]
+                top = list(zip(idx, val))
             else:   # top_k > 1024: dense scores + the full-sort selector (rare)
-                q_ptr, q_terms, q_w = pack_queries(packed)
                 dense = ix.score_dense(q_ptr, q_terms, q_w)
                 i2, v2 = fast_topk_selection(dense, min(k, n_docs))
                 top = [(i2[i].cpu().numpy(), v2[i].cpu().numpy()) for i in range(len(packed))]
@@ -255,12 +260,17 @@ class RetrievalService:
                     if len(self.query_cache) < 1000:
                         self.query_cache[cache_key] = (ti, tv)
                 res = self._to_result(ti, tv)
-                for qid in pending[cache_key]:
+                qids = pending[cache_key]
+                results[qids[0]] = res
+                for qid in qids[1:]:
                     results[qid] = dict(res)
         return {qid: results[qid] for qid in queries}
 
     def _to_result(self, indices, scores) -> Dict[str, float]:
-        return {self.doc_ids[int(i)]: float(s) for i, s in zip(indices, scores) if s > 0 and i >= 0}
+        ids = self.doc_ids
+        il = indices.tolist() if hasattr(indices, "tolist") else list(indices)
+        sl = scores.tolist() if hasattr(scores, "tolist") else list(scores)
+        return {ids[i]: s for i, s in zip(il, sl) if s > 0 and i >= 0}
 
     # ------------------------------------------------------------------ dense side (off the BM25 path)
     def _load_embeddings(self):
