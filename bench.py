@@ -236,7 +236,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import b200ret
-    from b200ret.dist import ShardedBM25, shard_range
+    from b200ret.dist import BatchPipeline, ShardedBM25, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -325,45 +325,24 @@ def run_b200(args):
     # the GPU mostly idle; with two batches in flight they run under the other batch's scoring kernel.  Each lane
     # has its own workspace (TermMajorIndex keeps one per stream), outputs and exchange buffers.
     depth = max(1, args.pipeline) if graphed else 1
-    lanes, lane_out = [], []
+    pipe, lane_out = None, []
     if depth > 1:
         try:
-            lanes = [ShardedBM25(ix) for _ in range(depth)]
-            lane_streams = [torch.cuda.Stream() for _ in range(depth)]
-            for lane, st_ in zip(lanes, lane_streams):       # eager first use: workspaces and exchange buffers
-                st_.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(st_):
-                    for _ in range(2):
-                        lane.search(d_ptr, d_terms, d_w, k)
-            torch.cuda.synchronize()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                G["pipe"] = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(G["pipe"], stream=side):
-                    for lane, st_ in zip(lanes, lane_streams):
-                        st_.wait_stream(side)
-                        with torch.cuda.stream(st_):
-                            lane_out.append(lane.search(d_ptr, d_terms, d_w, k))
-                    for st_ in lane_streams:
-                        side.wait_stream(st_)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
+            pipe = BatchPipeline(ix, depth)
+            lane_out = pipe.capture(d_ptr, d_terms, d_w, k)
             for _ in range(2):
-                G["pipe"].replay()
+                pipe.replay()
             torch.cuda.synchronize()
-            G["pipe_out"] = lane_out
         except Exception as ex:
             print(f"[bench] batch pipelining unavailable ({type(ex).__name__}: {ex}); one batch in flight",
                   file=sys.stderr)
-            depth, lanes, lane_out = 1, [], []
-            G.pop("pipe", None)
+            depth, pipe, lane_out = 1, None, []
             torch.cuda.synchronize()
 
     def run_steps(n):
         if depth > 1:
             for _ in range(n // depth):
-                G["pipe"].replay()
+                pipe.replay()
             for _ in range(n % depth):
                 step()
         else:
@@ -469,11 +448,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     step = eager_step = run_steps = None
     G.clear()
-    for lane in lanes:
-        if world > 1 and lane._peer is not None:
-            lane._peer.check()
-        lane.ix = None
-    lanes, lane_out = [], []
+    if pipe is not None:
+        if world > 1:
+            pipe.check()
+        pipe.close()
+    pipe, lane_out = None, []
     idx = val = None
     fused_info = (t_step.value, cap.value)
     exchange_kind = sharded.exchange

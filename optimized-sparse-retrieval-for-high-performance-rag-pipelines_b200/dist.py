@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "global_statistics", "gather_candidates", "merge_shard_candidates", "sharded_int8_scan",
-           "ShardedBM25", "PeerExchange"]
+           "ShardedBM25", "PeerExchange", "BatchPipeline"]
 
 
 def shard_range(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
@@ -200,3 +200,74 @@ class ShardedBM25:
                                                  val.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                                  _stream_ptr(dev)), "merge candidates")
         return idx, val
+
+
+class BatchPipeline:
+    """`depth` independent query batches in flight on `depth` CUDA streams, captured as ONE CUDA graph.
+
+    A search step is a dependent chain -- threshold sample, threshold, scoring, selection, candidate exchange -- whose
+    small kernels leave the GPU mostly idle (0.09 of 0.45 ms per step on a 1/8 shard of the 1M-doc corpus).  With a
+    second batch in flight they run under the other batch's scoring kernel, and that kernel's tail is filled too.
+    Every lane is a ShardedBM25 of its own over the SAME shard index: the index keeps one workspace per stream, the
+    lane owns its outputs and (multi-GPU) its exchange buffers, so the lanes never share mutable state.
+
+        pipe = BatchPipeline(index, depth=2)
+        outs = pipe.capture(q_ptr, q_terms, q_weights, k)    # [(idx, val)] per lane, device tensors (graph outputs)
+        ...write new queries into the captured input tensors (same shapes)...
+        pipe.replay()                                          # depth steps; results are in `outs`
+
+    All ranks of a doc-sharded job must capture and replay in step (the exchange is collective)."""
+
+    def __init__(self, shard_index, depth: int = 2, group=None):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.lanes = [ShardedBM25(shard_index, group) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(shard_index.device) for _ in range(depth)]
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.outputs = []
+
+    @property
+    def depth(self) -> int:
+        return len(self.lanes)
+
+    def capture(self, q_ptr: torch.Tensor, q_terms: torch.Tensor, q_weights: torch.Tensor, k: int):
+        """Capture one step per lane on (q_ptr, q_terms, q_weights): CUDA tensors that stay the graph's inputs."""
+        cur = torch.cuda.current_stream()
+        for lane, st in zip(self.lanes, self.streams):       # eager first use: workspaces and exchange buffers
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for _ in range(2):
+                    lane.search(q_ptr, q_terms, q_weights, k)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        self.outputs = []
+        with torch.cuda.stream(side):
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                for lane, st in zip(self.lanes, self.streams):
+                    st.wait_stream(side)
+                    with torch.cuda.stream(st):
+                        self.outputs.append(lane.search(q_ptr, q_terms, q_weights, k))
+                for st in self.streams:
+                    side.wait_stream(st)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        return self.outputs
+
+    def replay(self) -> None:
+        """Enqueue `depth` steps on the current stream."""
+        self.graph.replay()
+
+    def check(self) -> None:
+        for lane in self.lanes:
+            if lane._peer is not None:
+                lane._peer.check()
+
+    def close(self) -> None:
+        """Drop the graph (it references the process group's memory) and the lanes."""
+        self.graph = None
+        self.outputs = []
+        for lane in self.lanes:
+            lane.ix = None
+        self.lanes = []

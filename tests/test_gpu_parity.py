@@ -897,3 +897,58 @@ def test_exchange_merge_kernel_emulated_ranks_on_one_gpu(b2r, world, nq, k):
             wi = np.where(want_u != 0, (np.uint64(0xFFFFFFFF) - (want_u & np.uint64(0xFFFFFFFF))).astype(np.int64), -1)
             assert np.array_equal(io, wi), (rep, r)
             assert np.all(np.isneginf(vo[want_u == 0]))
+
+
+# ----------------------------------------------------------------------------------- batches in flight / threads
+def test_batch_pipeline_and_concurrent_host_searches(b2r):
+    """(1) dist.BatchPipeline: two batches in flight on two streams inside one captured graph give, lane by lane,
+    what a plain search gives, replay after replay, also after new queries were written into the captured inputs.
+    (2) RetrievalService-level thread safety (the reference's search_bm25 may be called from several threads): four
+    threads issue host-buffer searches on ONE index at the same time; every result equals the serial one."""
+    import threading
+    from b200ret import synthetic as S
+    from b200ret.dist import BatchPipeline
+    n_docs, n_vocab, k = 90_000, 9000, 10
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 50, seed=71)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+    sets = [S.zipf_queries(200, n_vocab, seed=72 + i) for i in range(4)]
+    want = [tuple(t.clone() for t in ix.search(*q, k)) for q in sets]
+    # (1) same shapes are needed for the captured inputs: pad every set's term arrays to the longest
+    n_t = max(len(q[1]) for q in sets)
+    dev = torch.device("cuda")
+    d_ptr = torch.from_numpy(sets[0][0]).to(dev)
+    d_terms = torch.zeros(n_t, dtype=torch.int32, device=dev)
+    d_w = torch.zeros(n_t, dtype=torch.float32, device=dev)
+    d_terms[:len(sets[0][1])] = torch.from_numpy(sets[0][1]).to(dev)
+    d_w[:len(sets[0][2])] = torch.from_numpy(sets[0][2]).to(dev)
+    pipe = BatchPipeline(ix, depth=2)
+    outs = pipe.capture(d_ptr, d_terms, d_w, k)
+    for rep, qi in enumerate((0, 0, 1, 2, 1)):
+        q = sets[qi]
+        d_ptr.copy_(torch.from_numpy(q[0]))
+        d_terms.zero_(); d_w.zero_()
+        d_terms[:len(q[1])] = torch.from_numpy(q[1]).to(dev)
+        d_w[:len(q[2])] = torch.from_numpy(q[2]).to(dev)
+        pipe.replay()
+        torch.cuda.synchronize()
+        for li, lv in outs:
+            assert torch.equal(li, want[qi][0]) and torch.equal(lv, want[qi][1]), (rep, qi)
+    pipe.close()
+    # (2)
+    res, errs = {}, []
+
+    def worker(i):
+        try:
+            for r in range(6):
+                q = sets[(i + r) % 4]
+                hi, hv = ix.search_host(q[0], q[1], q[2], k)
+                res[(i, r)] = (hi, hv, (i + r) % 4)
+        except Exception as ex:          # pragma: no cover
+            errs.append(ex)
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t_ in th: t_.start()
+    for t_ in th: t_.join()
+    assert not errs and len(res) == 24
+    for (i, r), (hi, hv, qi) in res.items():
+        assert np.array_equal(hi, want[qi][0].cpu().numpy()) and np.array_equal(_bits(hv), _bits(want[qi][1].cpu().numpy())), (i, r)
