@@ -230,14 +230,18 @@ class BatchPipeline:
     def depth(self) -> int:
         return len(self.lanes)
 
-    def capture(self, q_ptr: torch.Tensor, q_terms: torch.Tensor, q_weights: torch.Tensor, k: int):
-        """Capture one step per lane on (q_ptr, q_terms, q_weights): CUDA tensors that stay the graph's inputs."""
+    def capture(self, q_ptr, q_terms, q_weights, k: int):
+        """Capture one step per lane on (q_ptr, q_terms, q_weights): CUDA tensors that stay the graph's inputs.  Each of
+        the three may be ONE tensor (every lane reads the same batch) or a list with one tensor per lane."""
+        def per_lane(x):
+            return list(x) if isinstance(x, (list, tuple)) else [x] * self.depth
+        q_ptr, q_terms, q_weights = per_lane(q_ptr), per_lane(q_terms), per_lane(q_weights)
         cur = torch.cuda.current_stream()
-        for lane, st in zip(self.lanes, self.streams):       # eager first use: workspaces and exchange buffers
+        for i, (lane, st) in enumerate(zip(self.lanes, self.streams)):   # eager first use: workspaces, exchange buffers
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 for _ in range(2):
-                    lane.search(q_ptr, q_terms, q_weights, k)
+                    lane.search(q_ptr[i], q_terms[i], q_weights[i], k)
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -245,10 +249,10 @@ class BatchPipeline:
         with torch.cuda.stream(side):
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=side):
-                for lane, st in zip(self.lanes, self.streams):
+                for i, (lane, st) in enumerate(zip(self.lanes, self.streams)):
                     st.wait_stream(side)
                     with torch.cuda.stream(st):
-                        self.outputs.append(lane.search(q_ptr, q_terms, q_weights, k))
+                        self.outputs.append(lane.search(q_ptr[i], q_terms[i], q_weights[i], k))
                 for st in self.streams:
                     side.wait_stream(st)
         cur.wait_stream(side)
