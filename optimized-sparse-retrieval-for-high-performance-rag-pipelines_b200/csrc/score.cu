@@ -9,8 +9,8 @@
 // query index fastest, so CTAs resident at the same time work on the same doc tile and share its
 // posting blocks through L2; HBM sees each posting once per batch.
 //
-// Three epilogues.  DENSE writes the f32 score vector (the reference's return value).  MAXIMA and FUSED are
-// the search path, which never materialises scores: (1) every 64th / 16th doc tile is scored with the
+// Four epilogues.  DENSE writes the f32 score vector (the reference's return value).  MAXIMA, FUSED and EXHAUSTIVE
+// are the search path, which never materialises scores: (1) every 64th / 16th doc tile is scored with the
 // MAXIMA epilogue, which emits one maximum per lane (a group of <= tile_docs/256 documents); the k-th largest
 // of those group maxima is a lower bound T of the k-th best score of the whole shard (k groups, hence k
 // documents, reach it).  (2) ALL tiles are scored with the FUSED epilogue, which appends the few documents

@@ -952,3 +952,25 @@ def test_batch_pipeline_and_concurrent_host_searches(b2r):
     assert not errs and len(res) == 24
     for (i, r), (hi, hv, qi) in res.items():
         assert np.array_equal(hi, want[qi][0].cpu().numpy()) and np.array_equal(_bits(hv), _bits(want[qi][1].cpu().numpy())), (i, r)
+
+
+def test_drop_in_kernels_accept_a_query_vector_shorter_than_the_vocabulary(b2r):
+    """The reference skips CSR term ids >= len(query_tf) (`if term_idx < len(query_tf)`, retrieval.py:66): a query
+    vector shorter than the vocabulary must work on the drop-in simd_bm25_score / simd_tfidf_score too (the index is
+    built over every term id of the CSR; the tail terms can simply never be queried)."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab = 5000, 900
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 30, seed=81)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    rng = np.random.default_rng(82)
+    for n_short in (300, 1):
+        qtf = np.zeros(n_short, np.float32)
+        qtf[rng.integers(0, n_short, min(5, n_short))] = 1.0
+        qtf[0] = 2.0
+        want = c_oracle.bm25_scores(qtf, data, indices, indptr, dl, idf, 1.2, 0.75, avgdl)
+        got = b2r.simd_bm25_score(qtf, data, indices, indptr.astype(np.int32), dl, idf, 1.2, 0.75, avgdl)
+        assert np.array_equal(_bits(got), _bits(want)), n_short
+        want3 = c_oracle.tfidf_scores(qtf, data, indices, indptr, idf)
+        got3 = b2r.simd_tfidf_score(qtf, data, indices, indptr.astype(np.int32), idf)
+        assert np.array_equal(_bits(got3), _bits(want3)), n_short
+    b2r.clear_index_cache()
