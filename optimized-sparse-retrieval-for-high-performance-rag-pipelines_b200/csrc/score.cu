@@ -484,6 +484,12 @@ constexpr int FUSED_MAX_K = 128;
 
 static bool g_fused_enabled = true;
 static int g_fused_cap = 0;
+// B2R_SAMPLE_STEP: every step-th doc tile forms the threshold sample (default 64; tuning experiments only)
+static const int g_sample_step = [] {
+    const char *e = getenv("B2R_SAMPLE_STEP");
+    const int v = e ? atoi(e) : 0;
+    return v >= 2 && v <= 1024 ? v : 0;
+}();
 // optional CUDA-event bracket around the fused scoring launch (bench.py's roofline of the dominant kernel)
 static bool g_profile = false;
 static cudaEvent_t g_ev[2] = {nullptr, nullptr};
@@ -501,17 +507,18 @@ static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
     if (!p.on) return p;
     // The threshold is (about) the k-th best of a 1/r sample (r = n_tiles / n_sample <= step), so a query collects
     // ~ k * r candidates (negative-binomial: sigma ~ sqrt(k) * r); the cap is the power of two above mean + 6 sigma.
-    p.step = k <= 16 ? 64 : 16;
+    p.step = 64;   // (k <= 128: up to ~12.6 K expected candidates, the lists hold up to 16384)
+    if (g_sample_step > 0) p.step = g_sample_step;
     p.n_sample = (ix->n_tiles + p.step - 1) / p.step;
     {
         const double r = (double)ix->n_tiles / p.n_sample;
         const double want = k * r + 6.0 * sqrt((double)k) * r + k;
         p.cap = 256;
-        while (p.cap < want && p.cap < 4096) p.cap <<= 1;
+        while (p.cap < want && p.cap < 16384) p.cap <<= 1;
     }
     if (g_fused_cap > 0) {   // b2r_set_fused_cap: test hook (tiny lists force the exhaustive fallback)
         p.cap = g_fused_cap < k ? k : g_fused_cap;
-        if (p.cap > 4096) p.cap = 4096;
+        if (p.cap > 16384) p.cap = 16384;
     }
     p.n_groups = (int64_t)p.n_sample * SC_GROUPS_PER_TILE;
     // tile 0 is full (n_tiles >= 8) and holds min(tile_docs / 2, 256) non-empty groups

@@ -347,12 +347,12 @@ __device__ __forceinline__ void select_bin_256(const uint32_t *hist, uint32_t kk
 // largest key, the k keys at or above it are compacted and only those are sorted.  Keys are distinct (they carry
 // the document index), so exactly k survive.
 constexpr int TL_THREADS = 256;
-constexpr int TL_MAX = 4096;  // longest list (32 KB of shared memory)
+constexpr int TL_MAX = 16384;  // longest list (dynamic shared memory: 8 bytes per key, 128 KB at the maximum)
 
 __global__ void __launch_bounds__(TL_THREADS)
 topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__restrict__ cnt, int k, int min_cnt,
                      uint64_t *__restrict__ out, int64_t *__restrict__ idx_out, float *__restrict__ val_out) {
-    __shared__ uint64_t arr[TL_MAX];
+    extern __shared__ uint64_t arr[];   // [max(cap, 32)]
     __shared__ uint64_t best[B2R_TOPK_MAX_FAST];
     __shared__ uint32_t hist[256], wsum[8], s_bin, s_kk, s_n;
     const int row = blockIdx.x, tid = threadIdx.x;
@@ -415,7 +415,13 @@ int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, 
     if (n_rows == 0) return B2R_OK;
     B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap && k <= B2R_TOPK_MAX_FAST,
                   "top-k of lists: cap=%d / k=%d unsupported", cap, k);
-    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, 0, st>>>(lists, cap, cnt, k, min_cnt, keys_out, idx_out, val_out);
+    // the uncompacted path (c <= k) sorts in place: room for the power of two above k as well
+    int need = cap;
+    while (need < k || (need & (need - 1))) need = (need | (need - 1)) + 1;
+    const size_t smem = (size_t)(need < 32 ? 32 : need) * 8;
+    if (smem > 40 * 1024)
+        B2R_CUDA(cudaFuncSetAttribute(topk_of_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, smem, st>>>(lists, cap, cnt, k, min_cnt, keys_out, idx_out, val_out);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
