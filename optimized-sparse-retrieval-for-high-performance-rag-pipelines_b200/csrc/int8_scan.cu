@@ -1026,6 +1026,12 @@ struct I8Fused {
     int64_t n_tiles, n_sample;
 };
 static bool g_int8_fused = true;
+// B2R_INT8_SAMPLE_STEP: stride of the threshold sample for k > 16 (tuning experiments only)
+static const int g_i8_step_k100 = [] {
+    const char *e = getenv("B2R_INT8_SAMPLE_STEP");
+    const int v = e ? atoi(e) : 0;
+    return v >= 2 && v <= 256 ? v : 16;
+}();
 
 static I8Fused i8_fused_plan(int32_t n_q, int64_t n_docs, int dim, int k, bool shape_ok) {
     I8Fused p = {};
@@ -1033,13 +1039,13 @@ static I8Fused i8_fused_plan(int32_t n_q, int64_t n_docs, int dim, int k, bool s
     // >= 256 tiles: the first sample tiles are full, so at least 128 >= k group maxima exist
     p.on = g_int8_fused && g_int8_use_mma && shape_ok && k <= 128 && p.n_tiles >= 256 && dim > 0 && n_q >= 1;
     if (!p.on) return p;
-    p.step = k <= 16 ? 32 : 16;
+    p.step = k <= 16 ? 32 : g_i8_step_k100;
     p.n_sample = (p.n_tiles + p.step - 1) / p.step;
     {   // a query collects ~ k * r candidates, r = n_tiles / n_sample (sigma ~ sqrt(k) * r): cap = 2^m >= mean + 6 sigma
         const double r = (double)p.n_tiles / (double)p.n_sample;
         const double want = k * r + 6.0 * sqrt((double)k) * r + k;
         p.cap = 256;
-        while (p.cap < want && p.cap < 4096) p.cap <<= 1;
+        while (p.cap < want && p.cap < 16384) p.cap <<= 1;
     }
     return p;
 }
