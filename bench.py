@@ -8,7 +8,7 @@ N > 1 exchange + merge the per-shard candidates).  The 1M-document corpus is doc
 N ranks (strong scaling: the corpus is fixed, as the metric names it).  Prints ONE JSON line.
 
   value         queries/s with the index and the query batch resident in HBM (CUDA events, max over ranks); the K
-                steps run as K/2 replays of a captured graph that holds two independent batches on two streams
+                steps run as replays of a captured graph that holds three independent batches on three streams
                 (run.batches_in_flight; run.ms_per_step_one_batch_in_flight is the serial figure)
   e2e           the same through the host-buffer C-ABI call (pinned host queries -> H2D -> score ->
                 select -> D2H of ids+scores inside the timed region)
@@ -740,7 +740,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", type=int, default=1, help="0 = skip the C1 / C3 / C5 secondary measurements")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the timed step as a CUDA graph (0 = eager)")
-    ap.add_argument("--pipeline", type=int, default=2,
+    ap.add_argument("--pipeline", type=int, default=3,
                     help="independent batches in flight on separate streams inside the timed region (1 = none)")
     ap.add_argument("--n-queries", type=int, default=None, help="override the batch size (profiling only)")
     ap.add_argument("--bank-schedule", type=int, default=1,
