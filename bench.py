@@ -325,26 +325,33 @@ def run_b200(args):
     # the GPU mostly idle; with two batches in flight they run under the other batch's scoring kernel.  Each lane
     # has its own workspace (TermMajorIndex keeps one per stream), outputs and exchange buffers.
     depth = max(1, args.pipeline) if graphed else 1
-    pipe, lane_out = None, []
+    pipe, pipe_rem, lane_out = None, None, []
     if depth > 1:
         try:
             pipe = BatchPipeline(ix, depth)
             lane_out = pipe.capture(d_ptr, d_terms, d_w, k)
             for _ in range(2):
                 pipe.replay()
+            if args.steps % depth > 1:          # the last steps % depth steps of the timed region: a smaller pipeline
+                pipe_rem = BatchPipeline(ix, args.steps % depth)
+                lane_out = lane_out + pipe_rem.capture(d_ptr, d_terms, d_w, k)
+                pipe_rem.replay()
             torch.cuda.synchronize()
         except Exception as ex:
             print(f"[bench] batch pipelining unavailable ({type(ex).__name__}: {ex}); one batch in flight",
                   file=sys.stderr)
-            depth, pipe, lane_out = 1, None, []
+            depth, pipe, pipe_rem, lane_out = 1, None, None, []
             torch.cuda.synchronize()
 
     def run_steps(n):
         if depth > 1:
             for _ in range(n // depth):
                 pipe.replay()
-            for _ in range(n % depth):
-                step()
+            if n % depth > 1 and pipe_rem is not None and pipe_rem.depth == n % depth:
+                pipe_rem.replay()
+            else:
+                for _ in range(n % depth):
+                    step()
         else:
             for _ in range(n):
                 step()
@@ -478,11 +485,12 @@ def run_b200(args):
             G["e2e_pipe"].check()
         G["e2e_pipe"].close()
     G.clear()
-    if pipe is not None:
-        if world > 1:
-            pipe.check()
-        pipe.close()
-    pipe, lane_out = None, []
+    for p_ in (pipe, pipe_rem):
+        if p_ is not None:
+            if world > 1:
+                p_.check()
+            p_.close()
+    pipe, pipe_rem, lane_out = None, None, []
     idx = val = None
     fused_info = (t_step.value, cap.value)
     exchange_kind = sharded.exchange
