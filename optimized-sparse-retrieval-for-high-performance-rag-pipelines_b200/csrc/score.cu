@@ -507,14 +507,19 @@ static FusedPlan fused_plan(const b2r_index *ix, int k, bool want_scores) {
     if (!p.on) return p;
     // The threshold is (about) the k-th best of a 1/r sample (r = n_tiles / n_sample <= step), so a query collects
     // ~ k * r candidates (negative-binomial: sigma ~ sqrt(k) * r); the cap is the power of two above mean + 6 sigma.
-    p.step = 64;   // (k <= 128: up to ~12.6 K expected candidates, the lists hold up to 16384)
+    // every 64th tile; for k > 16 on shards of fewer than 1024 tiles every 16th (a handful of sample tiles gives a
+    // loose threshold, and the longer candidate lists then cost more in topk_of_lists than the sample saves)
+    p.step = (k <= 16 || ix->n_tiles >= 1024) ? 64 : 16;
     if (g_sample_step > 0) p.step = g_sample_step;
     p.n_sample = (ix->n_tiles + p.step - 1) / p.step;
     {
         const double r = (double)ix->n_tiles / p.n_sample;
         const double want = k * r + 6.0 * sqrt((double)k) * r + k;
         p.cap = 256;
-        while (p.cap < want && p.cap < 16384) p.cap <<= 1;
+        while (p.cap < want && p.cap < 4096) p.cap <<= 1;
+        // beyond 4096 keys in steps of 1024: the list is staged in shared memory by topk_of_lists, whose occupancy
+        // follows the capacity
+        if (want > 4096) p.cap = want >= 16384 ? 16384 : (int)((want + 1023) / 1024) * 1024;
     }
     if (g_fused_cap > 0) {   // b2r_set_fused_cap: test hook (tiny lists force the exhaustive fallback)
         p.cap = g_fused_cap < k ? k : g_fused_cap;

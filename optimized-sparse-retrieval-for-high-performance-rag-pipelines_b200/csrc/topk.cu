@@ -415,10 +415,10 @@ int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, 
     if (n_rows == 0) return B2R_OK;
     B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap && k <= B2R_TOPK_MAX_FAST,
                   "top-k of lists: cap=%d / k=%d unsupported", cap, k);
-    // the uncompacted path (c <= k) sorts in place: room for the power of two above k as well
-    int need = cap;
-    while (need < k || (need & (need - 1))) need = (need | (need - 1)) + 1;
-    const size_t smem = (size_t)(need < 32 ? 32 : need) * 8;
+    // the uncompacted path (c <= k) sorts in place: room for the power of two above k (>= 32) as well
+    int pk = 32;
+    while (pk < k) pk <<= 1;
+    const size_t smem = (size_t)(cap > pk ? cap : pk) * 8;
     if (smem > 40 * 1024)
         B2R_CUDA(cudaFuncSetAttribute(topk_of_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, smem, st>>>(lists, cap, cnt, k, min_cnt, keys_out, idx_out, val_out);
