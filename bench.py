@@ -605,10 +605,27 @@ def run_secondary(args, world, rank, dev, timed):
         d_q = [torch.from_numpy(a).to(dev) for a in (q_ptr, q_terms, q_w)]
         for _ in range(3):
             idx, val = sh.search(*d_q, k)
-        ms = timed(lambda: sh.search(*d_q, k), steps) / steps
+        ms_eager = timed(lambda: sh.search(*d_q, k), steps) / steps
         ws_bytes = int(ix._ws.numel()) if ix._ws is not None else 0
+        # the same step with two batches in flight (dist.BatchPipeline: one captured graph = two steps on two streams)
+        ms, in_flight = ms_eager, 1
+        try:
+            from b200ret.dist import BatchPipeline
+            pipe = BatchPipeline(ix, 2)
+            lanes = pipe.capture(*d_q, k)
+            pipe.replay()
+            torch.cuda.synchronize()
+            if all(torch.equal(a, idx) and torch.equal(b_, val) for a, b_ in lanes):
+                ms = timed(pipe.replay, steps) / (2 * steps)
+                in_flight = 2
+            if world > 1:
+                pipe.check()
+            pipe.close()
+        except Exception as ex:
+            print(f"[bench] C3: batch pipelining unavailable ({type(ex).__name__}: {ex})", file=sys.stderr)
         rec = {"workload": f"c3: synthetic Zipfian 8.8M docs x 100K vocab, 1024-query batch, BM25 top-100, doc-sharded "
                            f"x{world}", "ms_per_step": ms, "queries_per_s": nq / (ms * 1e-3), "n_gpus": world,
+               "batches_in_flight": in_flight, "ms_per_step_one_batch_eager": ms_eager,
                "postings_touched_per_step": int(df[q_terms].sum()), "index_bytes_rank0": ix.device_bytes(),
                "workspace_bytes_rank0": ws_bytes}
         if rank == 0:
