@@ -18,7 +18,8 @@ N ranks (strong scaling: the corpus is fixed, as the metric names it).  Prints O
   parity        every query of the timed configuration against the oracle (N = 1: all of them, N > 1: 64)
   secondary     driver-visible timings + parity of the other BASELINE configs: C1 (FiQA-shape text corpus through
                 RetrievalService.search_bm25, tokeniser included), C3 (8.8M docs, top-100, this job's N GPUs),
-                C5 (INT8 10M x 768 scan, top-100, sharded over this job's N GPUs)
+                C4 (SPLADE-shape impact index, 8.8M docs x 120 nnz, one GPU), C5 (INT8 10M x 768 scan, top-100,
+                sharded over this job's N GPUs)
   cpu_baseline  the reference's per-query loop on the host cores, on a bounded sample of the same queries:
                 kind "reference" = the reference's own Numba kernels (oracle/_ref, when the recipe
                 oracle/make_ref.py could run), kind "port" = oracle/bm25_oracle.c (C + OpenMP restatement)
@@ -691,6 +692,51 @@ def run_secondary(args, world, rank, dev, timed):
         torch.cuda.empty_cache()
     except Exception as ex:
         sec["c5_int8_10m_top100"] = {"error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- C4: SPLADE-shape impact index at its named size, 8.8M docs x 30,522 vocab x 120 nnz/doc (1.056e9 postings),
+    #      256 weighted 30-term queries, impact dot top-10 (rank 0; BASELINE names no sharding for this config)
+    if rank == 0:
+        try:
+            n_docs, n_vocab, k, nq = 8_800_000, 30522, 10, 256
+            data, ind, ptr, _ = zipf_csr_torch(n_docs, n_vocab, 0, 20260103, dev, distinct_per_doc=120, chunk=1 << 18)
+            idf1 = np.ones(n_vocab, np.float32)
+            q_ptr, q_terms, q_w = S.impact_queries(nq, n_vocab, 30)
+            ix = b200ret.TermMajorIndex.from_csr(data, ind, ptr, None, n_vocab=n_vocab, idf=idf1, kind="impact")
+            df = torch.bincount(ind, minlength=n_vocab).cpu().numpy()
+            nc = 4
+            host = [t.cpu().numpy() for t in (data, ind, ptr)]
+            del data, ind, ptr
+            torch.cuda.empty_cache()
+            d_q = [torch.from_numpy(a).to(dev) for a in (q_ptr, q_terms, q_w)]
+            for _ in range(2):
+                idx, val = ix.search(*d_q, k)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(steps):
+                ix.search(*d_q, k)
+            b_.record()
+            torch.cuda.synchronize()
+            ms = a_.elapsed_time(b_) / steps
+            from oracle import c_oracle
+            c_oracle.use_all_host_threads()
+            ok = True
+            for q in range(nc):
+                qtf = np.zeros(n_vocab, np.float32)
+                qtf[q_terms[q_ptr[q]:q_ptr[q + 1]]] = q_w[q_ptr[q]:q_ptr[q + 1]]
+                wi, wv = c_oracle.topk(c_oracle.tfidf_scores(qtf, host[0], host[1], host[2], idf1), k)
+                ok &= bool(np.array_equal(idx[q].cpu().numpy(), wi) and
+                           np.array_equal(_bits(val[q].cpu().numpy()), _bits(_fold(wv))))
+            sec["c4_splade_8p8m_top10"] = {
+                "workload": "c4: SPLADE-shape 8.8M docs x 30,522 vocab, 120 nnz/doc (1.056e9 postings), 256 queries of 30 "
+                            "weighted terms, impact dot top-10, one GPU", "ms_per_step": ms,
+                "queries_per_s": nq / (ms * 1e-3), "postings_touched_per_step": int(df[q_terms].sum()),
+                "index_bytes": ix.device_bytes(),
+                "parity": {"queries_checked": nc, "ids_and_scores": True, "bit_exact_vs_oracle": ok}}
+            del ix, host, d_q
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            sec["c4_splade_8p8m_top10"] = {"error": f"{type(ex).__name__}: {ex}"}
 
     # ---- C1: FiQA-shape text corpus through RetrievalService (rank 0; tokeniser and dict building included)
     if rank == 0:
