@@ -617,8 +617,9 @@ def run_secondary(args, world, rank, dev, timed):
             pipe.replay()
             torch.cuda.synchronize()
             if all(torch.equal(a, idx) and torch.equal(b_, val) for a, b_ in lanes):
-                ms = timed(pipe.replay, steps) / (2 * steps)
-                in_flight = 2
+                ms_pipe = timed(pipe.replay, steps) / (2 * steps)
+                if ms_pipe < ms_eager:          # (on one GPU the chain is a small part of a 24 ms step: keep the better)
+                    ms, in_flight = ms_pipe, 2
             if world > 1:
                 pipe.check()
             pipe.close()
