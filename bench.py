@@ -377,8 +377,31 @@ def run_b200(args):
     h2d = int(w["q_ptr"].nbytes + w["q_terms"].nbytes + w["q_w"].nbytes)
     d2h = int(nq * k * (8 + 4))
     if world == 1:
-        e2e_step = lambda: ix.search_host(w["q_ptr"], w["q_terms"], w["q_w"], k)  # noqa: E731
-        e2e_api = "b2r_search_batch_host (C ABI, host buffers in / host buffers out)"
+        # the reference-facing call: b2r_search_batch_host, HOST buffers in and out.  Two host threads, each with its
+        # own handle on the resident index (own pinned staging, workspace, CUDA stream), keep two calls in flight, as a
+        # server would: one call's copies and launch gaps run under the other's scoring kernel.
+        from concurrent.futures import ThreadPoolExecutor
+        n_thr = 2 if args.pipeline > 1 else 1
+        views = [ix.view() for _ in range(n_thr)]
+        thr_streams = [torch.cuda.Stream() for _ in range(n_thr)]
+        pool = ThreadPoolExecutor(max_workers=n_thr)
+        G["e2e_pool"] = pool
+
+        def _host_call(i):
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(thr_streams[i]):
+                return views[i].search_host(w["q_ptr"], w["q_terms"], w["q_w"], k)
+
+        def e2e_step():
+            res = list(pool.map(_host_call, range(n_thr)))
+            return res
+        e2e_step.steps_per_call = n_thr
+        e2e_check = e2e_step()
+        for hi_, hv_ in e2e_check:       # what the host call returns must be what the timed step produced
+            if not (np.array_equal(hi_, got_idx) and np.array_equal(_bits(hv_), _bits(got_val))):
+                print("PARITY FAILURE: host-buffer call differs from the device-buffer step", file=sys.stderr)
+        e2e_api = ("b2r_search_batch_host (C ABI, host buffers in / host buffers out), %d host thread(s) with one call "
+                   "in flight each" % n_thr)
     else:
         hp, ht, hw = (torch.from_numpy(w[n]).pin_memory() for n in ("q_ptr", "q_terms", "q_w"))
         oi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
@@ -481,6 +504,8 @@ def run_b200(args):
     # the captured graph references the communicator and the index buffers: drop it before anything else
     torch.cuda.synchronize()
     step = eager_step = run_steps = e2e_step = None
+    if G.get("e2e_pool") is not None:
+        G["e2e_pool"].shutdown()
     if G.get("e2e_pipe") is not None:
         if world > 1:
             G["e2e_pipe"].check()

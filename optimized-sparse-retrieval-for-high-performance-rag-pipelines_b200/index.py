@@ -282,6 +282,17 @@ class TermMajorIndex:
         d.dense_id, d.dense_ptr, d.n_dense_max = b_["dense_id"].data_ptr(), b_["dense_ptr"].data_ptr(), int(hdr.n_dense_max)
         return self
 
+    def view(self) -> "TermMajorIndex":
+        """A second handle on the SAME device buffers with its own pinned staging buffers, workspaces and lock: lets
+        several host threads run search_host concurrently (each on its own CUDA stream) against one resident index."""
+        v = TermMajorIndex()
+        for name in ("device", "kind", "n_docs", "n_vocab", "nnz", "tile_docs", "n_tiles", "doc_id_base", "k1", "b",
+                     "avgdl", "idf_host", "workspace_cap_bytes"):
+            setattr(v, name, getattr(self, name))
+        v._bufs = self._bufs                    # shared, immutable after the build
+        C.memmove(C.byref(v._desc), C.byref(self._desc), C.sizeof(self._desc))
+        return v
+
     # ------------------------------------------------------------------ properties
     @property
     def padded_docs(self) -> int:
