@@ -250,6 +250,7 @@ def run_b200(args):
     w = make_workload(args.workload, args.n_queries)
     n_docs, k = w["n_docs"], w["k"]
     b200ret.set_bank_schedule(bool(args.bank_schedule))
+    b200ret.set_approx_prefilter(bool(args.prefilter))
     lo, hi = shard_range(n_docs, world, rank)
     s, e = w["indptr"][lo], w["indptr"][hi]
     ix = b200ret.TermMajorIndex.from_csr(w["data"][s:e], w["indices"][s:e], w["indptr"][lo:hi + 1] - s, w["dl"][lo:hi],
@@ -377,31 +378,14 @@ def run_b200(args):
     h2d = int(w["q_ptr"].nbytes + w["q_terms"].nbytes + w["q_w"].nbytes)
     d2h = int(nq * k * (8 + 4))
     if world == 1:
-        # the reference-facing call: b2r_search_batch_host, HOST buffers in and out.  Two host threads, each with its
-        # own handle on the resident index (own pinned staging, workspace, CUDA stream), keep two calls in flight, as a
-        # server would: one call's copies and launch gaps run under the other's scoring kernel.
-        from concurrent.futures import ThreadPoolExecutor
-        n_thr = 2 if args.pipeline > 1 else 1
-        views = [ix.view() for _ in range(n_thr)]
-        thr_streams = [torch.cuda.Stream() for _ in range(n_thr)]
-        pool = ThreadPoolExecutor(max_workers=n_thr)
-        G["e2e_pool"] = pool
-
-        def _host_call(i):
-            torch.cuda.set_device(local)
-            with torch.cuda.stream(thr_streams[i]):
-                return views[i].search_host(w["q_ptr"], w["q_terms"], w["q_w"], k)
-
-        def e2e_step():
-            res = list(pool.map(_host_call, range(n_thr)))
-            return res
-        e2e_step.steps_per_call = n_thr
-        e2e_check = e2e_step()
-        for hi_, hv_ in e2e_check:       # what the host call returns must be what the timed step produced
-            if not (np.array_equal(hi_, got_idx) and np.array_equal(_bits(hv_), _bits(got_val))):
-                print("PARITY FAILURE: host-buffer call differs from the device-buffer step", file=sys.stderr)
-        e2e_api = ("b2r_search_batch_host (C ABI, host buffers in / host buffers out), %d host thread(s) with one call "
-                   "in flight each" % n_thr)
+        # the reference-facing call: b2r_search_batch_host, HOST buffers in and out, one call at a time (two host
+        # threads with one call in flight each were measured and are slower: 2.90 vs 2.82 ms per step on one box --
+        # the hand-off between Python threads costs more than the overlap gains)
+        e2e_step = lambda: ix.search_host(w["q_ptr"], w["q_terms"], w["q_w"], k)  # noqa: E731
+        hi_, hv_ = e2e_step()
+        if not (np.array_equal(hi_, got_idx) and np.array_equal(_bits(hv_), _bits(got_val))):
+            print("PARITY FAILURE: host-buffer call differs from the device-buffer step", file=sys.stderr)
+        e2e_api = "b2r_search_batch_host (C ABI, host buffers in / host buffers out)"
     else:
         hp, ht, hw = (torch.from_numpy(w[n]).pin_memory() for n in ("q_ptr", "q_terms", "q_w"))
         oi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
@@ -468,6 +452,7 @@ def run_b200(args):
     lib.b2r_set_profiling(1)
     k_times = []
     dense = None
+    prefiltered = False
     if fused:
         for _ in range(3 + args.steps):
             eager_step()
@@ -476,7 +461,8 @@ def run_b200(args):
             k_times.append(t_ms.value)
         k_ms = float(np.mean(k_times[3:]))
         alg_bytes = 12 * postings          # fused epilogue writes no score vector
-        kernel_name = "score_tiles_kernel<BM25, FUSED>"
+        prefiltered = bool(args.prefilter) and "post_pk" in ix._bufs
+        kernel_name = "score_approx_kernel<FUSED>" if prefiltered else "score_tiles_kernel<BM25, FUSED>"
     else:
         dense = torch.empty((nq, ix.padded_docs), dtype=torch.float32, device=dev)
         score_only = lambda: ix.score_dense(d_ptr, d_terms, d_w, out=dense)  # noqa: E731
@@ -504,8 +490,6 @@ def run_b200(args):
     # the captured graph references the communicator and the index buffers: drop it before anything else
     torch.cuda.synchronize()
     step = eager_step = run_steps = e2e_step = None
-    if G.get("e2e_pool") is not None:
-        G["e2e_pool"].shutdown()
     if G.get("e2e_pipe") is not None:
         if world > 1:
             G["e2e_pipe"].check()
@@ -566,6 +550,8 @@ def run_b200(args):
                     "postings_touched_per_step_rank0": postings, "cuda_graph_replay": graphed,
                     "batches_in_flight": depth, "ms_per_step_one_batch_in_flight": ms_single / args.steps,
                     "launches_per_step": launches_per_step,
+                    "prefilter": ("f32 pre-filter on 4-byte packed postings (score_approx_kernel), survivors rescored with "
+                                  "the exact f64 chain before ranking" if prefiltered else "off: every posting scored in f64"),
                     "selection": ("fused: threshold = k-th largest group maximum of every %dth tile, all tiles scored with "
                                   "the candidate epilogue, cap %d" % fused_info)
                     if fused else "plain: score vector + streaming select"},
@@ -840,6 +826,8 @@ def main():
     ap.add_argument("--pipeline", type=int, default=3,
                     help="independent batches in flight on separate streams inside the timed region (1 = none)")
     ap.add_argument("--n-queries", type=int, default=None, help="override the batch size (profiling only)")
+    ap.add_argument("--prefilter", type=int, default=1,
+                    help="0 = score every posting in f64 (round-1 kernel) instead of the f32 pre-filter + exact rescoring")
     ap.add_argument("--bank-schedule", type=int, default=1,
                     help="0 = build the index without the bank schedule of dense segments (A/B measurement only)")
     args = ap.parse_args()

@@ -85,6 +85,8 @@ typedef struct b2r_index {
     uint32_t *dense_ptr; /* [n_dense_max * (n_tiles * B2R_SUBTILES + 1)] */
     int32_t n_dense_max; /* rows allocated in dense_ptr (from b2r_index_sizes_for) */
     int32_t reserved0;
+    uint32_t *post_pk;   /* optional (BM25, tile_docs == 4096): b2r_index_pack_bytes(nnz) bytes filled by b2r_index_pack;
+                            NULL = the search path scores in f64 only */
 } b2r_index;
 
 typedef struct b2r_index_sizes {
@@ -116,6 +118,21 @@ int b2r_index_build(const b2r_index *ix, const float *tf, const int32_t *indices
                     size_t scratch_bytes, void *stream);
 /* Synchronises the stream and reports malformed input (term id out of range) found by the build. */
 int b2r_index_build_status(const void *scratch, void *stream);
+
+/* Packed copy of a BM25 index for the approximate pre-filter of the search path (csrc/score_approx.cu): 4 bytes per
+ * posting -- the f32 bits of post_val rounded to 11 explicit mantissa bits | the 12-bit document offset inside its
+ * tile -- plus a 256-byte trailer (largest magnitude, "not finite" flag).  b2r_search_batch then scores every posting
+ * in f32 from this copy, keeps the documents that can still be in the top-k under a proven per-query error bound and
+ * rescores only those with the f64 chain of post_val: results are bit-identical to the f64-only path, which stays in
+ * use for dense score output, impact indexes, other tile sizes and as the exhaustive fallback.  The copy is derived
+ * data: it is not part of the index file; call b2r_index_pack after b2r_index_build or after loading a file.
+ * b2r_index_pack_status synchronises and returns B2R_ERR_UNSUPPORTED when a value is not finite (the caller then
+ * clears ix->post_pk); *u_max_out (optional) receives the largest packed magnitude. */
+size_t b2r_index_pack_bytes(int64_t nnz);
+int b2r_index_pack(const b2r_index *ix, void *stream);
+int b2r_index_pack_status(const b2r_index *ix, void *stream, float *u_max_out);
+/* Test / profiling hook: 0 = b2r_search_batch ignores post_pk (f64 scoring of every posting, as before). */
+void b2r_set_approx_prefilter(int enabled);
 
 /* ---- On-disk form of a b2r_index (the reference only caches the doc-major CSR as
  * an .npz, evaluate_rag_pipeline.py:280-312).  One file = this header (4096 bytes) followed by the six device

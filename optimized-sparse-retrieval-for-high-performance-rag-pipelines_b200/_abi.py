@@ -35,6 +35,7 @@ class B2RIndex(C.Structure):
         ("dense_ptr", C.c_void_p),
         ("n_dense_max", C.c_int32),
         ("reserved0", C.c_int32),
+        ("post_pk", C.c_void_p),
     ]
 
 
@@ -92,6 +93,10 @@ SIGNATURES = {
     "b2r_index_sizes_for": (C.c_int, [_I64, _I64, _I32, _I32, _I32, C.POINTER(B2RIndexSizes)]),
     "b2r_index_build": (C.c_int, [_PIX, _P, _P, _P, _P, _F64, _F64, _F64, _P, _SZ, _P]),
     "b2r_index_build_status": (C.c_int, [_P, _P]),
+    "b2r_index_pack_bytes": (_SZ, [_I64]),
+    "b2r_index_pack": (C.c_int, [_PIX, _P]),
+    "b2r_index_pack_status": (C.c_int, [_PIX, _P, C.POINTER(C.c_float)]),
+    "b2r_set_approx_prefilter": (None, [C.c_int]),
     "b2r_checksum64": (C.c_uint64, [_P, _SZ]),
     "b2r_index_file_layout": (C.c_int, [C.POINTER(B2RIndexFileHeader), C.POINTER(C.c_uint64)]),
     "b2r_index_file_check": (C.c_int, [C.POINTER(B2RIndexFileHeader), C.c_uint64]),

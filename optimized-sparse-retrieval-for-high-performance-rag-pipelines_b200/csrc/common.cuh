@@ -119,6 +119,18 @@ int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t
 // idx_out / val_out (optional): the decoded form of the ranked keys (-1 / -inf for "no candidate"); keys_out may be null.
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
                   uint64_t *keys_out, cudaStream_t st, int64_t *idx_out = nullptr, float *val_out = nullptr);
+// approximate pre-filter of the BM25 search path (score_approx.cu): drop-in replacements of the MAXIMA launch, the
+// FUSED launch and topk_of_lists of the f64 fused path; the exhaustive fallback gate (cnt > cap) is shared
+bool approx_usable(const b2r_index *ix, int k);
+int approx_maxima(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
+                  const float *idf, int q0, int nq, int tile_step, int n_sample, float *maxima, int64_t maxima_stride,
+                  cudaStream_t st);
+int approx_fused(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
+                 const float *idf, int q0, int nq, const uint64_t *thr, uint64_t *cand, int32_t *cand_cnt, int cap,
+                 cudaStream_t st);
+int approx_select(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
+                  const float *idf, int q0, int nq, const uint64_t *thr, const uint64_t *cand, int32_t *cand_cnt,
+                  int cap, int k, uint64_t *keys_out, int64_t *idx_out, float *val_out, cudaStream_t st);
 int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
                 int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st);
 

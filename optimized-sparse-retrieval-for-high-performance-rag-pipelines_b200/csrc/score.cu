@@ -681,11 +681,19 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
         if (fp.on) {
             // 1. threshold: group maxima of every step-th tile, then the k-th largest of them per query (the same
             //    kernel resets the query's candidate and fallback counters)
-            ScoreOut so = {};
-            so.scores = maxima;
-            so.scores_stride = fp.n_groups;
-            so.n_docs = (uint32_t)ix->n_docs;
-            rc = launch_score<SC_OUT_MAXIMA>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
+            // (with a packed copy of the index, steps 1-3 run on the f32 pre-filter of score_approx.cu: same launches,
+            //  same buffers, bit-identical results)
+            const bool approx = approx_usable(ix, k);
+            if (approx) {
+                rc = approx_maxima(ix, q_ptr, q_terms, q_weights, idf, (int)q0, nq, fp.step, fp.n_sample, maxima,
+                                   fp.n_groups, st);
+            } else {
+                ScoreOut so = {};
+                so.scores = maxima;
+                so.scores_stride = fp.n_groups;
+                so.n_docs = (uint32_t)ix->n_docs;
+                rc = launch_score<SC_OUT_MAXIMA>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
+            }
             if (rc) return rc;
             rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, true, thr, st, cand_cnt, x_done);
             if (rc) return rc;
@@ -698,13 +706,21 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             fo.n_docs = (uint32_t)ix->n_docs;
             fo.doc_id_base = (uint32_t)ix->doc_id_base;
             if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[0], st));
-            rc = launch_score<SC_OUT_FUSED>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, fo);
+            if (approx)
+                rc = approx_fused(ix, q_ptr, q_terms, q_weights, idf, (int)q0, nq, thr, cand, cand_cnt, fp.cap, st);
+            else
+                rc = launch_score<SC_OUT_FUSED>(L, (int)q0, nq, SC_TILES_ALL, 1, ix->n_tiles, fo);
             if (rc) return rc;
             if (g_profile) B2R_CUDA(cudaEventRecord(g_ev[1], st));
             // 3. exact top-k of the candidates, ranked keys and their decoded form in one launch; a list that
             //    overflowed or came up short marks its query (cand_cnt > cap)
-            rc = topk_of_lists(cand, nq, fp.cap, cand_cnt, k, k, kout, st, idx_out ? idx_out + q0 * k : nullptr,
-                               val_out ? val_out + q0 * k : nullptr);
+            if (approx)   // (the candidates carry approximate scores: the survivors are rescored in f64 before ranking)
+                rc = approx_select(ix, q_ptr, q_terms, q_weights, idf, (int)q0, nq, thr, cand, cand_cnt, fp.cap, k,
+                                   kout, idx_out ? idx_out + q0 * k : nullptr, val_out ? val_out + q0 * k : nullptr,
+                                   st);
+            else
+                rc = topk_of_lists(cand, nq, fp.cap, cand_cnt, k, k, kout, st, idx_out ? idx_out + q0 * k : nullptr,
+                                   val_out ? val_out + q0 * k : nullptr);
             if (rc) return rc;
             // 4. exact fallback for the marked queries only (every other CTA leaves at once): exhaustive scoring with
             //    a streaming top-k in shared memory -- no score vector, no workspace that grows with the corpus

@@ -12,6 +12,8 @@ libb200ret.so through the C ABI.  The doc-major scipy CSR the reference builds
   dense_id  i32[V]     row of dense_ptr for terms averaging >= 64 postings per tile, else -1
   dense_ptr u32[...]   per dense term: offsets of its postings per sub-tile (8 sub-tiles per tile)
   idf       f32[V]
+  post_pk   u32[nnz]   (BM25, 4096-doc tiles) packed copy for the f32 pre-filter of the search path: the f32 bits of
+                       post_val rounded to 11 mantissa bits | the 12-bit doc offset in its tile (csrc/score_approx.cu)
 """
 from __future__ import annotations
 
@@ -25,7 +27,13 @@ import torch
 from . import _abi
 
 __all__ = ["TermMajorIndex", "pack_queries", "queries_from_dense", "reference_idf", "reference_avgdl",
-           "set_fused_selection", "set_fused_cap"]
+           "set_fused_selection", "set_fused_cap", "set_approx_prefilter"]
+
+
+def set_approx_prefilter(enabled: bool) -> None:
+    """Profiling / test hook: False makes search score every posting in f64 (the round-1 kernel) even when the index
+    carries the packed copy for the f32 pre-filter (results are bit-identical either way)."""
+    _abi.lib.b2r_set_approx_prefilter(1 if enabled else 0)
 
 
 def set_fused_cap(cap: int) -> None:
@@ -126,16 +134,18 @@ class TermMajorIndex:
         self._pinned = {}
         self._lock = threading.Lock()
         self.workspace_cap_bytes = 16 << 30
+        self.prefilter_u_max: Optional[float] = None   # largest packed value when the f32 pre-filter copy exists
 
     # ------------------------------------------------------------------ build
     @classmethod
     def from_csr(cls, data, indices, indptr, doc_lengths=None, *, n_vocab: int, idf=None, avgdl=None,
                  k1: float = 1.2, b: float = 0.75, kind: str = "bm25", doc_id_base: int = 0,
-                 tile_docs: int = 4096, device=None) -> "TermMajorIndex":
+                 tile_docs: int = 4096, device=None, prefilter: bool = True) -> "TermMajorIndex":
         """Build from a doc-major CSR (numpy arrays or CUDA tensors).
 
         idf / avgdl default to the reference's host expressions over THIS CSR; a doc-sharded build
-        passes the global values instead (see dist.py).
+        passes the global values instead (see dist.py).  prefilter=False skips the packed copy of the search
+        path's f32 pre-filter (an index that only serves dense score output does not need it).
         """
         self = cls()
         dev = self.device = _cuda_device(device)
@@ -194,7 +204,28 @@ class TermMajorIndex:
                                             scratch.numel(), st), "index build")
         _abi.check(_abi.lib.b2r_index_build_status(scratch.data_ptr(), st), "index build")
         del tf_d, ind_d, ptr_d, dl_d, scratch
+        if prefilter:
+            self._pack_prefilter()
         return self
+
+    def _pack_prefilter(self) -> None:
+        """Derive the packed copy the search path's f32 pre-filter reads (BM25 with 4096-document tiles only; it
+        is derived data: never saved, rebuilt here after a build or a load)."""
+        if self.kind != "bm25" or self.tile_docs != 4096 or self.nnz == 0:
+            return
+        d = self._desc
+        buf = torch.empty(int(_abi.lib.b2r_index_pack_bytes(self.nnz)), dtype=torch.uint8, device=self.device)
+        d.post_pk = buf.data_ptr()
+        st = _stream_ptr(self.device)
+        _abi.check(_abi.lib.b2r_index_pack(C.byref(d), st), "index pack")
+        u_max = C.c_float(0.0)
+        rc = _abi.lib.b2r_index_pack_status(C.byref(d), st, C.byref(u_max))
+        if rc == -4:                 # B2R_ERR_UNSUPPORTED: a value is not finite -- f64 scoring only
+            d.post_pk = None
+            return
+        _abi.check(rc, "index pack")
+        self._bufs["post_pk"] = buf
+        self.prefilter_u_max = float(u_max.value)
 
     # ------------------------------------------------------------------ on-disk form (SURVEY 8 f1)
     _IO_CHUNK = 64 << 20
@@ -280,6 +311,7 @@ class TermMajorIndex:
         d.n_vocab, d.tile_docs, d.n_tiles, d.kind = self.n_vocab, self.tile_docs, self.n_tiles, int(hdr.kind)
         d.post_doc, d.post_val, d.blk_ptr = b_["post_doc"].data_ptr(), b_["post_val"].data_ptr(), b_["blk_ptr"].data_ptr()
         d.dense_id, d.dense_ptr, d.n_dense_max = b_["dense_id"].data_ptr(), b_["dense_ptr"].data_ptr(), int(hdr.n_dense_max)
+        self._pack_prefilter()
         return self
 
     def view(self) -> "TermMajorIndex":

@@ -104,7 +104,7 @@ def _cached_index(kind, data, indices, indptr, doc_lengths, n_vocab, k1, b, avgd
             n_vocab = max(int(n_vocab), top)
         ones = np.ones(n_vocab, np.float32)   # idf is a per-call input: set below
         ix = TermMajorIndex.from_csr(data, indices, indptr, doc_lengths, n_vocab=n_vocab, idf=ones,
-                                     avgdl=avgdl, k1=k1, b=b, kind=kind)
+                                     avgdl=avgdl, k1=k1, b=b, kind=kind, prefilter=False)   # dense scores only
         _INDEX_CACHE[key] = (ix, (data, indices, indptr, doc_lengths))
         while len(_INDEX_CACHE) > _INDEX_CACHE_MAX:
             _INDEX_CACHE.popitem(last=False)

@@ -974,3 +974,108 @@ def test_drop_in_kernels_accept_a_query_vector_shorter_than_the_vocabulary(b2r):
         got3 = b2r.simd_tfidf_score(qtf, data, indices, indptr.astype(np.int32), idf)
         assert np.array_equal(_bits(got3), _bits(want3)), n_short
     b2r.clear_index_cache()
+
+
+# ----------------------------------------------------------------------------------- f32 pre-filter of the search path
+def test_approx_prefilter_equals_f64_path_and_oracle(b2r, tmp_path):
+    """The search path's f32 pre-filter (packed 4-byte postings, f32 accumulators, exact f64 rescoring of the survivors;
+    csrc/score_approx.cu) must return bit for bit what the f64-only path and the oracle return: Zipfian queries (normal
+    mode, negative idf on the head terms), rare-term queries (positive mode: few matches), long queries (> 32 terms),
+    an empty query, absurd weights (no finite error bound -> exhaustive fallback), fractional tf / lengths, several k,
+    a shard with a document-id base, forced list overflow, and an index that went through save() / load()."""
+    from b200ret import synthetic as S
+    n_docs, n_vocab = 120_000 + 123, 6000                   # 30 tiles of 4096 -> the fused path is active
+    data, indices, indptr, dl = S.zipf_corpus(n_docs, n_vocab, 50, seed=71)
+    rng = np.random.default_rng(72)
+    data = (data * rng.uniform(0.25, 1.75, len(data))).astype(np.float32)       # fractional term frequencies
+    dl = (dl * rng.uniform(0.5, 1.5, len(dl))).astype(np.float32)
+    idf = b2r.reference_idf(indices, n_docs, n_vocab); avgdl = b2r.reference_avgdl(dl)
+    assert (idf[:5] < 0).all()                               # head terms occur in most documents: negative idf
+    z_ptr, z_terms, z_w = S.zipf_queries(150, n_vocab, seed=73)
+    u_ptr, u_terms, u_w = S.zipf_queries(40, n_vocab, seed=74, uniform=True)
+    qs = [(z_terms[z_ptr[i]:z_ptr[i + 1]], z_w[z_ptr[i]:z_ptr[i + 1]] * (1 + i % 3)) for i in range(150)]
+    qs += [(u_terms[u_ptr[i]:u_ptr[i + 1]], u_w[u_ptr[i]:u_ptr[i + 1]] * 0.5) for i in range(40)]
+    qs += [(rng.choice(n_vocab, size=int(rng.integers(33, 80)), replace=False), np.ones(80, np.float32)[:0])
+           for _ in range(6)]
+    qs = [(t_, w_ if len(w_) == len(t_) else np.ones(len(t_), np.float32)) for t_, w_ in qs]
+    qs += [([], []),                                          # no terms: all-zero scores, lowest ids
+           ([0, 1, 2], [1.0, 1.0, 1.0]),                      # only negative-idf terms: every touched score <= 0
+           ([3, 900, 4100], [1e30, 1e30, 1e30]),              # no finite bound: exact fallback
+           ([5, 1200, 5000], [1e-30, 1e-30, 1e-30]),          # tiny weights
+           ([n_vocab - 1], [2.0])]                            # one rare term
+    q_ptr, q_terms, q_w = b2r.pack_queries(qs)
+    args = (data, indices, indptr, dl, idf, 1.2, 0.75, avgdl)
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+    assert "post_pk" in ix._bufs and ix.prefilter_u_max is not None and 0 < ix.prefilter_u_max < 2.3
+    path = str(tmp_path / "ix.b2r")
+    ix.save(path)
+    loaded = b2r.TermMajorIndex.load(path)
+    assert "post_pk" in loaded._bufs                          # derived data: rebuilt on load, never stored
+    for k in (1, 10, 100):
+        wi, wv = _oracle_topk(args, q_ptr, q_terms, q_w, k)
+        wv = np.where(wv == 0, np.float32(0), wv)
+        ai, av, ak = ix.search(q_ptr, q_terms, q_w, k, return_keys=True)
+        b2r.set_approx_prefilter(False)
+        try:
+            fi, fv, fk = ix.search(q_ptr, q_terms, q_w, k, return_keys=True)
+        finally:
+            b2r.set_approx_prefilter(True)
+        bad = np.flatnonzero((ai != fi).any(1).cpu().numpy())
+        assert torch.equal(ai, fi) and torch.equal(av, fv) and torch.equal(ak, fk), (k, bad[:10])
+        assert np.array_equal(ai.cpu().numpy(), wi), k
+        assert np.array_equal(_bits(av.cpu().numpy()), _bits(wv)), k
+        li, lv = loaded.search(q_ptr, q_terms, q_w, k)
+        assert torch.equal(li, ai) and torch.equal(lv, av), k
+        hi_, hv_ = ix.search_host(q_ptr, q_terms, q_w, k)
+        assert np.array_equal(hi_, wi) and np.array_equal(_bits(hv_), _bits(wv)), k
+    # forced overflow: every query goes through the exhaustive f64 fallback behind the pre-filter
+    k = 10
+    wi, wv = _oracle_topk(args, q_ptr, q_terms, q_w, k)
+    b2r.set_fused_cap(1)
+    try:
+        xi, xv = ix.search(q_ptr, q_terms, q_w, k)
+    finally:
+        b2r.set_fused_cap(0)
+    assert np.array_equal(xi.cpu().numpy(), wi) and np.array_equal(_bits(xv.cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
+    # a shard with a document-id base: keys carry global ids
+    lo, hi = 40_000, n_docs
+    s, e = indptr[lo], indptr[hi]
+    sh = b2r.TermMajorIndex.from_csr(data[s:e], indices[s:e], indptr[lo:hi + 1] - s, dl[lo:hi], n_vocab=n_vocab,
+                                     idf=idf, avgdl=avgdl, doc_id_base=lo)
+    si, sv = sh.search(q_ptr, q_terms, q_w, k)
+    b2r.set_approx_prefilter(False)
+    try:
+        ti, tv = sh.search(q_ptr, q_terms, q_w, k)
+    finally:
+        b2r.set_approx_prefilter(True)
+    assert torch.equal(si, ti) and torch.equal(sv, tv) and int(si.min()) >= lo
+
+
+def test_approx_prefilter_mass_ties_and_non_finite_values(b2r):
+    """Identical documents (thousands of equal scores around the k-th best: more survivors than the rescoring stage
+    holds -> exhaustive fallback, ties broken by document index) and an index whose saturation factors are not finite
+    (doc length NaN: the packed copy is refused and the f64 path serves the index)."""
+    n_docs, n_vocab, k = 60_000, 50, 10
+    indptr = np.arange(0, 2 * n_docs + 1, 2, dtype=np.int64)
+    indices = np.tile(np.array([3, 7], np.int32), n_docs)
+    data = np.ones(2 * n_docs, np.float32)
+    data[2 * 31_000] = 2.0                                   # one document stands out
+    dl = np.full(n_docs, 2.0, np.float32)
+    idf = np.linspace(0.5, 2.0, n_vocab).astype(np.float32); avgdl = 2.0
+    q_ptr, q_terms, q_w = b2r.pack_queries([([3, 7], [1.0, 1.0]), ([3], [1.0]), ([9], [1.0])])
+    ix = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+    assert "post_pk" in ix._bufs
+    idx, val = ix.search(q_ptr, q_terms, q_w, k)
+    wi, wv = _oracle_topk((data, indices, indptr, dl, idf, 1.2, 0.75, avgdl), q_ptr, q_terms, q_w, k)
+    assert np.array_equal(idx.cpu().numpy(), wi) and np.array_equal(_bits(val.cpu().numpy()), _bits(np.where(wv == 0, np.float32(0), wv)))
+    assert idx[0, 0].item() == 31_000 and idx[0, 1:].tolist() == list(range(9))
+    dl2 = dl.copy(); dl2[17] = np.nan
+    ix2 = b2r.TermMajorIndex.from_csr(data, indices, indptr, dl2, n_vocab=n_vocab, idf=idf, avgdl=avgdl)
+    assert "post_pk" not in ix2._bufs and not ix2._desc.post_pk
+    i2, v2 = ix2.search(q_ptr, q_terms, q_w, k)
+    b2r.set_fused_selection(False)
+    try:
+        p2, pv2 = ix2.search(q_ptr, q_terms, q_w, k)
+    finally:
+        b2r.set_fused_selection(True)
+    assert torch.equal(i2, p2) and np.array_equal(_bits(v2.cpu().numpy()), _bits(pv2.cpu().numpy()))
