@@ -249,7 +249,7 @@ def run_b200(args):
 
     w = make_workload(args.workload, args.n_queries)
     n_docs, k = w["n_docs"], w["k"]
-    b200ret.set_bank_schedule(bool(args.bank_schedule))
+    b200ret.set_bank_schedule(int(args.bank_schedule))
     b200ret.set_approx_prefilter(bool(args.prefilter))
     lo, hi = shard_range(n_docs, world, rank)
     s, e = w["indptr"][lo], w["indptr"][hi]

@@ -110,15 +110,18 @@ size_t topk_keys_ws_bytes(int64_t n_rows, int64_t n, int32_t k);  // for topk_ke
 // 2^-20 relative so that it stays a valid bound for the exact scores (INT8 scan).
 // positive_floor = true: a threshold score <= 0 is replaced by "strictly positive scores only" (the caller must
 // then gate on short lists: topk_of_lists(min_cnt = k)).
-// zero_a / zero_b (optional): int32[n_rows] counters the kernel resets to 0 for its row.
+// zero_a / zero_b (optional): int32[n_rows] counters the kernel resets to 0 for its row; zero_scalar (optional): one
+// int32 reset by the first row's CTA (the number of marked rows, see topk_of_lists).
 int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
                   bool positive_floor, uint64_t *thr_out, cudaStream_t st, int32_t *zero_a = nullptr,
-                  int32_t *zero_b = nullptr);
+                  int32_t *zero_b = nullptr, int32_t *zero_scalar = nullptr);
 // keys_out[row, 0..k) = the k best of the first min(cnt[row], cap) keys of lists[row, 0..cap) (0-padded); cap <= 4096.
 // Rows with cnt[row] < min_cnt get cnt[row] = cap + 1, i.e. they are marked like overflowed rows for the fallback gate.
 // idx_out / val_out (optional): the decoded form of the ranked keys (-1 / -inf for "no candidate"); keys_out may be null.
+// marked (optional): int32[1 + n_rows]; every marked row (overflowed or short) appends its index: marked[1 + marked[0]++].
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
-                  uint64_t *keys_out, cudaStream_t st, int64_t *idx_out = nullptr, float *val_out = nullptr);
+                  uint64_t *keys_out, cudaStream_t st, int64_t *idx_out = nullptr, float *val_out = nullptr,
+                  int32_t *marked = nullptr);
 // approximate pre-filter of the BM25 search path (score_approx.cu): drop-in replacements of the MAXIMA launch, the
 // FUSED launch and topk_of_lists of the f64 fused path; the exhaustive fallback gate (cnt > cap) is shared
 bool approx_usable(const b2r_index *ix, int k);
@@ -130,7 +133,8 @@ int approx_fused(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_ter
                  cudaStream_t st);
 int approx_select(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
                   const float *idf, int q0, int nq, const uint64_t *thr, const uint64_t *cand, int32_t *cand_cnt,
-                  int cap, int k, uint64_t *keys_out, int64_t *idx_out, float *val_out, cudaStream_t st);
+                  int cap, int k, uint64_t *keys_out, int64_t *idx_out, float *val_out, int32_t *marked,
+                  cudaStream_t st);
 int decode_keys(const uint64_t *keys, int64_t n, int64_t *idx_out, float *val_out, const float *scores,
                 int64_t row_stride, int32_t k, int64_t doc_id_base, cudaStream_t st);
 

@@ -315,9 +315,13 @@ dense_fill_kernel(const uint32_t *__restrict__ blk_ptr, const uint32_t *__restri
 // round-robin over the 16 residue classes: posting number j of class r goes to row j, rows are packed.
 // Every full row is conflict-free; only the tail, where some classes are exhausted, still replays.
 constexpr int SCHED_THREADS = 128;
-constexpr int SCHED_SLOTS = 16;   // 8-byte accumulator slots per 128-byte bank row
+constexpr int SCHED_SLOTS_MAX = 32;
+// SLOTS = 16: residue classes doc mod 16 (8-byte accumulator slots per 128-byte bank row: the f64 scorer).
+// SLOTS = 32: classes doc mod 32, rows in class order -- a full row of 32 postings hits 32 different 4-byte banks
+// (the f32 pre-filter of score_approx.cu) AND its two halves (classes 0..15, 16..31) are distinct mod 16, so the
+// f64 scorer's half-warps stay conflict-free as well.
 
-template <int KIND>
+template <int KIND, int SLOTS>
 __global__ void __launch_bounds__(SCHED_THREADS)
 bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__restrict__ dense_ptr, int n_tiles,
                      int tile_docs, uint32_t *__restrict__ post_doc, void *__restrict__ post_val) {
@@ -327,7 +331,7 @@ bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__res
     if (id < 0) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n_warps = SCHED_THREADS / 32;
     const int sub = tile_docs / B2R_SUBTILES, words = sub >> 5;
-    const size_t per_warp = (size_t)sub * (sizeof(val_t) + 4) + (size_t)words * 4 + SCHED_SLOTS * 4;
+    const size_t per_warp = (size_t)sub * (sizeof(val_t) + 4) + (size_t)words * 4 + SCHED_SLOTS_MAX * 4;
     unsigned char *mine = sched_smem + (size_t)wib * ((per_warp + 15) / 16 * 16);
     val_t *s_val = reinterpret_cast<val_t *>(mine);
     uint32_t *s_doc = reinterpret_cast<uint32_t *>(mine + (size_t)sub * sizeof(val_t));
@@ -338,7 +342,7 @@ bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__res
     const uint32_t *row = dense_ptr + (size_t)id * (n_seg + 1);
     for (size_t seg = wib; seg < n_seg; seg += n_warps) {
         const uint32_t lo = row[seg], n = row[seg + 1] - lo;
-        if (n <= SCHED_SLOTS || n > (uint32_t)sub) continue;  // one group: nothing to gain (n > sub: bad input, flagged)
+        if (n <= (uint32_t)SLOTS || n > (uint32_t)sub) continue;  // one group: nothing to gain (n > sub: bad input, flagged)
         const uint32_t doc0 = (uint32_t)seg * (uint32_t)sub;
         for (int w = lane; w < words; w += 32) bitmap[w] = 0;
         __syncwarp();
@@ -350,23 +354,24 @@ bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__res
             atomicOr(&bitmap[l >> 5], 1u << (l & 31));
         }
         __syncwarp();
-        if (lane < SCHED_SLOTS) {
+        if (lane < SLOTS) {
+            const uint32_t m = SLOTS == 16 ? (0x00010001u << lane) : (1u << lane);
             uint32_t c = 0;
-            for (int w = 0; w < words; ++w) c += __popc(bitmap[w] & (0x00010001u << lane));
+            for (int w = 0; w < words; ++w) c += __popc(bitmap[w] & m);
             cls_cnt[lane] = c;
         }
         __syncwarp();
         for (uint32_t i = lane; i < n; i += 32) {
             const uint32_t d = s_doc[i];
             const uint32_t l = (d - doc0) & (uint32_t)(sub - 1);
-            const uint32_t r = l & (SCHED_SLOTS - 1), wl = l >> 5;
-            const uint32_t cls = 0x00010001u << r;
+            const uint32_t r = l & (uint32_t)(SLOTS - 1), wl = l >> 5;
+            const uint32_t cls = SLOTS == 16 ? (0x00010001u << r) : (1u << r);
             uint32_t j = 0;  // postings of my class that precede me
             for (uint32_t w = 0; w < wl; ++w) j += __popc(bitmap[w] & cls);
-            if (l & 16) j += (bitmap[wl] >> r) & 1u;
+            if (SLOTS == 16 && (l & 16)) j += (bitmap[wl] >> r) & 1u;
             uint32_t pos = 0;  // rows 0..j-1 in full, then the classes below mine that reach row j
 #pragma unroll
-            for (int c = 0; c < SCHED_SLOTS; ++c) {
+            for (int c = 0; c < SLOTS; ++c) {
                 const uint32_t cc = cls_cnt[c];
                 pos += min(cc, j) + ((uint32_t)c < r && cc > j ? 1u : 0u);
             }
@@ -379,7 +384,17 @@ bank_schedule_kernel(const int32_t *__restrict__ dense_id, const uint32_t *__res
     }
 }
 
-static bool g_bank_schedule = true;
+static int g_bank_schedule = 32;   // 0 = off, 16 / 32 = residue classes (b2r_set_bank_schedule)
+
+template <int KIND, int SLOTS>
+static int launch_bank_schedule(const b2r_index *ix, size_t smem, cudaStream_t st) {
+    B2R_CUDA(cudaFuncSetAttribute(bank_schedule_kernel<KIND, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    bank_schedule_kernel<KIND, SLOTS><<<(unsigned)ix->n_vocab, SCHED_THREADS, smem, st>>>(
+        ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, ix->post_doc, ix->post_val);
+    B2R_LAUNCH_CHECK();
+    return B2R_OK;
+}
 
 // postings per tile from which a term gets sub-tile offsets (B2R_DENSE_MIN overrides it: tuning experiments only)
 static int dense_min_per_tile() {
@@ -516,27 +531,26 @@ extern "C" int b2r_index_build(const b2r_index *ix, const float *tf, const int32
         if (g_bank_schedule) {
             const int sub = ix->tile_docs / B2R_SUBTILES;
             const size_t vb = ix->kind == B2R_KIND_BM25 ? 8 : 4;
-            const size_t per_warp = ((size_t)sub * (vb + 4) + (size_t)(sub >> 5) * 4 + SCHED_SLOTS * 4 + 15) / 16 * 16;
+            const size_t per_warp = ((size_t)sub * (vb + 4) + (size_t)(sub >> 5) * 4 + SCHED_SLOTS_MAX * 4 + 15) / 16 * 16;
             const size_t smem = per_warp * (SCHED_THREADS / 32);
-            if (ix->kind == B2R_KIND_BM25) {
-                B2R_CUDA(cudaFuncSetAttribute(bank_schedule_kernel<B2R_KIND_BM25>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                bank_schedule_kernel<B2R_KIND_BM25><<<(unsigned)ix->n_vocab, SCHED_THREADS, smem, st>>>(
-                    ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, ix->post_doc, ix->post_val);
-            } else {
-                B2R_CUDA(cudaFuncSetAttribute(bank_schedule_kernel<B2R_KIND_IMPACT>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                bank_schedule_kernel<B2R_KIND_IMPACT><<<(unsigned)ix->n_vocab, SCHED_THREADS, smem, st>>>(
-                    ix->dense_id, ix->dense_ptr, ix->n_tiles, ix->tile_docs, ix->post_doc, ix->post_val);
-            }
-            B2R_LAUNCH_CHECK();
+            // 32 classes need sub-tiles of at least 64 documents to be worth a row; smaller tiles keep 16
+            const bool wide = g_bank_schedule == 32 && sub >= 64;
+            int rc2;
+            if (ix->kind == B2R_KIND_BM25)
+                rc2 = wide ? launch_bank_schedule<B2R_KIND_BM25, 32>(ix, smem, st)
+                           : launch_bank_schedule<B2R_KIND_BM25, 16>(ix, smem, st);
+            else
+                rc2 = wide ? launch_bank_schedule<B2R_KIND_IMPACT, 32>(ix, smem, st)
+                           : launch_bank_schedule<B2R_KIND_IMPACT, 16>(ix, smem, st);
+            if (rc2) return rc2;
         }
     }
     return B2R_OK;
 }
 
 // test / profiling hook: 0 = keep the dense segments doc-ascending (no bank schedule); applies to later builds
-extern "C" void b2r_set_bank_schedule(int enabled) { b2r::g_bank_schedule = enabled != 0; }
+// (16 = residue classes doc mod 16 only, the round-1 schedule; any other non-zero value = the default, 32 classes)
+extern "C" void b2r_set_bank_schedule(int enabled) { b2r::g_bank_schedule = enabled == 0 ? 0 : (enabled == 16 ? 16 : 32); }
 
 extern "C" int b2r_index_build_status(const void *scratch, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);

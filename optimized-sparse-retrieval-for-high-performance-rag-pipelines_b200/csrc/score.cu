@@ -145,7 +145,7 @@ __device__ __forceinline__ void apply_term(int dense, uint32_t beg, uint32_t end
 enum { SC_OUT_DENSE = 0, SC_OUT_FUSED = 1, SC_OUT_MAXIMA = 2, SC_OUT_EXHAUSTIVE = 3 };
 constexpr int SC_XK_CAP = 8192;    // EXHAUSTIVE: keys a CTA keeps in shared memory (k best so far + pending candidates)
 constexpr int SC_XK_CHUNK = 4096;  // EXHAUSTIVE: documents examined between two capacity checks
-constexpr int SC_X_PARTS = 8;      // EXHAUSTIVE: CTAs per query, each with its own share of the doc tiles
+constexpr int SC_X_PARTS = 32;     // EXHAUSTIVE: most CTAs per query, each with its own share of the doc tiles
 enum { SC_TILES_ALL = 0, SC_TILES_SAMPLE = 1 };
 constexpr int SC_GROUPS_PER_TILE = 32 * B2R_SUBTILES;  // MAXIMA: one group maximum per lane
 
@@ -163,7 +163,11 @@ struct ScoreOut {
     int32_t cap;
     uint32_t n_docs;        // documents in this shard (tail of the last tile is padding)
     uint32_t doc_id_base;
-    // EXHAUSTIVE (runs for queries with gate[q] > gate_cap): exact top-k with no score vector
+    // EXHAUSTIVE: exact top-k with no score vector for the queries the selection kernels marked (overflowed or short
+    // candidate list): marked[0] = their number, marked[1 + i] = their indices inside the chunk.  A fixed, small grid
+    // walks the work items (marked query, part): an unmarked batch costs one wave of CTAs that read one integer.
+    const int32_t *marked;
+    int32_t x_n_parts;      // parts a marked query's doc tiles are split into (<= SC_X_PARTS)
     int32_t k;
     uint64_t *x_parts;      // [queries, SC_X_PARTS, k] the k best of every part's tiles
     int32_t *x_done;        // [queries] parts finished (zeroed by the caller); the last one merges
@@ -187,9 +191,11 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     __shared__ __align__(8) uint64_t zbar[B2R_SUBTILES];  // per warp: "my accumulators have been cleared"
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int ql = blockIdx.x;  // query index inside this launch's chunk
-    const int q = q0 + ql;
-    if ((OUT == SC_OUT_DENSE || OUT == SC_OUT_EXHAUSTIVE) && o.gate != nullptr && o.gate[ql] <= o.gate_cap) return;
+    if (OUT == SC_OUT_DENSE && o.gate != nullptr && o.gate[blockIdx.x] <= o.gate_cap) return;
+    // work items: every other epilogue has exactly one per CTA, (query blockIdx.x, tiles blockIdx.y + i gridDim.y);
+    // EXHAUSTIVE loops over (marked query, part) pairs
+    const int n_items = OUT == SC_OUT_EXHAUSTIVE ? o.marked[0] * o.x_n_parts : 1;
+    const int y_stride = OUT == SC_OUT_EXHAUSTIVE ? o.x_n_parts : (int)gridDim.y;
     // EXHAUSTIVE: the CTA's k best keys so far live sorted in xk[0, x_kept), pending candidates behind them
     uint64_t *xk = reinterpret_cast<uint64_t *>(acc + tile_docs);
     __shared__ int x_cnt, x_last;
@@ -207,13 +213,6 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         }
         __syncthreads();
     };
-    if (OUT == SC_OUT_EXHAUSTIVE) {
-        if (threadIdx.x == 0) {
-            x_cnt = 0;
-            x_thr = 0ull;
-        }
-        __syncthreads();
-    }
     const int sub = tile_docs / B2R_SUBTILES;
     double *acc_w = acc + w * sub;
     const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
@@ -224,6 +223,19 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     }
     __syncwarp();
     uint32_t zphase = 0;
+  for (int item = OUT == SC_OUT_EXHAUSTIVE ? (int)blockIdx.x : 0; item < n_items;
+       item += OUT == SC_OUT_EXHAUSTIVE ? (int)gridDim.x : 1) {
+    const int ql = OUT == SC_OUT_EXHAUSTIVE ? o.marked[1 + item / o.x_n_parts] : (int)blockIdx.x;  // query inside the chunk
+    const int y_first = OUT == SC_OUT_EXHAUSTIVE ? item % o.x_n_parts : (int)blockIdx.y;
+    const int q = q0 + ql;
+    if (OUT == SC_OUT_EXHAUSTIVE) {
+        __syncthreads();   // (the previous item's shared state is no longer read)
+        if (threadIdx.x == 0) {
+            x_cnt = 0;
+            x_thr = 0ull;
+        }
+        __syncthreads();
+    }
     const int qs = q_ptr[q], qe = q_ptr[q + 1];
     auto tile_of = [&](int y) -> int {
         return tile_mode == SC_TILES_ALL ? y : y * tile_step;
@@ -244,13 +256,13 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         const int32_t did = dense_id[t];
         my_dense = did >= 0;
         my_row = my_dense ? dense_ptr + (size_t)did * dense_row + w : blk_ptr + (size_t)t * n_tiles;
-        if ((int)blockIdx.y < n_y) {
-            const size_t i0 = (size_t)tile_of(blockIdx.y) * (my_dense ? B2R_SUBTILES : 1);
+        if (y_first < n_y) {
+            const size_t i0 = (size_t)tile_of(y_first) * (my_dense ? B2R_SUBTILES : 1);
             nxt_beg = my_row[i0];
             nxt_end = my_row[i0 + 1];
         }
     }
-  for (int y = blockIdx.y; y < n_y; y += gridDim.y) {
+  for (int y = y_first; y < n_y; y += y_stride) {
     if (lane == 0) {  // clear my sub-tile's accumulators with one bulk copy; overlaps the term staging below
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar_a), "r"((uint32_t)(sub * 8))
                      : "memory");
@@ -264,8 +276,8 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
     const uint32_t my_doc0 = (uint32_t)tile * (uint32_t)tile_docs + (uint32_t)w * (uint32_t)sub;
     const size_t my_sub = (size_t)tile * B2R_SUBTILES + w;
     uint32_t my_beg = nxt_beg, my_end = nxt_end;
-    if (staged && my_row != nullptr && y + (int)gridDim.y < n_y) {  // offsets of the next tile: used one iteration later
-        const size_t i1 = (size_t)tile_of(y + gridDim.y) * (my_dense ? B2R_SUBTILES : 1);
+    if (staged && my_row != nullptr && y + y_stride < n_y) {  // offsets of the next tile: used one iteration later
+        const size_t i1 = (size_t)tile_of(y + y_stride) * (my_dense ? B2R_SUBTILES : 1);
         nxt_beg = my_row[i1];
         nxt_end = my_row[i1 + 1];
     }
@@ -395,16 +407,16 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
         __syncthreads();
         x_compact();
         const int k = o.k;
-        uint64_t *mine = o.x_parts + ((int64_t)ql * gridDim.y + blockIdx.y) * k;
+        uint64_t *mine = o.x_parts + ((int64_t)ql * y_stride + y_first) * k;
         for (int i = threadIdx.x; i < k; i += SC_THREADS) mine[i] = i < x_cnt ? xk[i] : 0ull;
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) x_last = atomicAdd(o.x_done + ql, 1) == (int)gridDim.y - 1;
+        if (threadIdx.x == 0) x_last = atomicAdd(o.x_done + ql, 1) == y_stride - 1;
         __syncthreads();
-        if (!x_last) return;
+        if (!x_last) continue;   // (CTA-uniform)
         __threadfence();
-        const int n = (int)gridDim.y * k;   // <= SC_X_PARTS * 128 keys
-        const uint64_t *all = o.x_parts + (int64_t)ql * gridDim.y * k;
+        const int n = y_stride * k;   // <= SC_X_PARTS * 128 keys
+        const uint64_t *all = o.x_parts + (int64_t)ql * y_stride * k;
         for (int i = threadIdx.x; i < n; i += SC_THREADS) xk[i] = __ldcg(all + i);
         if (threadIdx.x == 0) x_cnt = n;
         __syncthreads();
@@ -417,6 +429,7 @@ score_tiles_kernel(const uint32_t *__restrict__ post_doc, const void *__restrict
             if (o.val_final) o.val_final[at] = key ? unord_f32((uint32_t)(key >> 32)) : __int_as_float(0xff800000);
         }
     }
+  }  // work items
 }
 
 struct ScoreLaunch {
@@ -444,10 +457,11 @@ static int launch_score(const ScoreLaunch &L, int q0, int nq, int tile_mode, int
     int per_cta = g_tiles_per_cta;
     while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 6 * 4) per_cta >>= 1;
     int grid_y = (OUT == SC_OUT_DENSE && o.gate != nullptr) ? (n_y < 4 ? n_y : 4) : (n_y + per_cta - 1) / per_cta;
-    // EXHAUSTIVE: normally every CTA leaves at once, so the grid is kept small on small shards (a marked query is then
-    // walked by fewer, longer-running CTAs: one part per 32 doc tiles, at most SC_X_PARTS)
-    if (OUT == SC_OUT_EXHAUSTIVE) grid_y = n_y / 32 < 1 ? 1 : (n_y / 32 > SC_X_PARTS ? SC_X_PARTS : n_y / 32);
-    dim3 grid((unsigned)nq, (unsigned)grid_y);
+    // EXHAUSTIVE: a fixed grid (two 96 KB CTAs per SM) walks the (marked query, part) work items; normally there are
+    // none and every CTA leaves after reading the count.  A marked query's doc tiles are split into one part per 8
+    // tiles, at most SC_X_PARTS: what the step waits for is the latency of the few marked queries.
+    if (OUT == SC_OUT_EXHAUSTIVE) grid_y = 1;
+    dim3 grid((unsigned)(OUT == SC_OUT_EXHAUSTIVE ? 148 * 2 : nq), (unsigned)grid_y);
     if (ix->kind == B2R_KIND_BM25) {
         auto kern = score_tiles_kernel<B2R_KIND_BM25, OUT>;
         B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -539,7 +553,7 @@ static size_t pass_bytes(const b2r_index *ix, const FusedPlan &fp, int64_t qc, i
     if (!fp.on) return align_up((size_t)padded_docs(ix) * 4 * (size_t)qc, 256) + topk_ws_bytes(qc, ix->n_docs, k);
     return align_up((size_t)fp.n_groups * 4 * (size_t)qc, 256) + align_up((size_t)qc * 8, 256) +
            align_up((size_t)qc * fp.cap * 8, 256) + 2 * align_up((size_t)qc * 4, 256) +
-           align_up((size_t)qc * SC_X_PARTS * k * 8, 256) + 256;
+           align_up((size_t)qc * SC_X_PARTS * k * 8, 256) + align_up((size_t)(qc + 1) * 4, 256) + 256;
 }
 
 }  // namespace b2r
@@ -661,7 +675,7 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
     void *tk_full = nullptr;
     size_t tk_full_bytes = 0;
     uint64_t *thr = nullptr, *cand = nullptr, *x_parts = nullptr;
-    int32_t *cand_cnt = nullptr, *x_done = nullptr;
+    int32_t *cand_cnt = nullptr, *x_done = nullptr, *marked = nullptr;
     if (fp.on) {
         maxima = static_cast<float *>(carve((size_t)fp.n_groups * 4 * (size_t)qc));
         thr = static_cast<uint64_t *>(carve((size_t)qc * 8));
@@ -669,6 +683,7 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
         cand_cnt = static_cast<int32_t *>(carve((size_t)qc * 4));
         x_done = static_cast<int32_t *>(carve((size_t)qc * 4));
         x_parts = static_cast<uint64_t *>(carve((size_t)qc * SC_X_PARTS * k * 8));
+        marked = static_cast<int32_t *>(carve((size_t)(qc + 1) * 4));
     } else {
         full = static_cast<float *>(carve((size_t)pad * 4 * (size_t)qc));
         tk_full_bytes = topk_ws_bytes(qc, ix->n_docs, k);
@@ -695,7 +710,7 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
                 rc = launch_score<SC_OUT_MAXIMA>(L, (int)q0, nq, SC_TILES_SAMPLE, fp.step, fp.n_sample, so);
             }
             if (rc) return rc;
-            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, true, thr, st, cand_cnt, x_done);
+            rc = kth_of_maxima(maxima, nq, fp.n_groups, fp.n_groups, k, false, true, thr, st, cand_cnt, x_done, marked);
             if (rc) return rc;
             // 2. every tile: score, keep only the documents that reach the threshold
             ScoreOut fo = {};
@@ -717,16 +732,16 @@ extern "C" int b2r_search_batch(const b2r_index *ix, const int32_t *q_ptr, const
             if (approx)   // (the candidates carry approximate scores: the survivors are rescored in f64 before ranking)
                 rc = approx_select(ix, q_ptr, q_terms, q_weights, idf, (int)q0, nq, thr, cand, cand_cnt, fp.cap, k,
                                    kout, idx_out ? idx_out + q0 * k : nullptr, val_out ? val_out + q0 * k : nullptr,
-                                   st);
+                                   marked, st);
             else
                 rc = topk_of_lists(cand, nq, fp.cap, cand_cnt, k, k, kout, st, idx_out ? idx_out + q0 * k : nullptr,
-                                   val_out ? val_out + q0 * k : nullptr);
+                                   val_out ? val_out + q0 * k : nullptr, marked);
             if (rc) return rc;
             // 4. exact fallback for the marked queries only (every other CTA leaves at once): exhaustive scoring with
             //    a streaming top-k in shared memory -- no score vector, no workspace that grows with the corpus
             ScoreOut xo = {};
-            xo.gate = cand_cnt;
-            xo.gate_cap = fp.cap;
+            xo.marked = marked;
+            xo.x_n_parts = ix->n_tiles / 8 < 1 ? 1 : (ix->n_tiles / 8 > SC_X_PARTS ? SC_X_PARTS : ix->n_tiles / 8);
             xo.n_docs = (uint32_t)ix->n_docs;
             xo.doc_id_base = (uint32_t)ix->doc_id_base;
             xo.k = k;

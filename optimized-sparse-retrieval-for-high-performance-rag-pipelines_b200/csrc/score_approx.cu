@@ -7,21 +7,25 @@
 // The exact scorer (score.cu) spends its time on the shared-memory pipe: an f64 read-modify-write per posting, fed by
 // 12 B of posting data.  Selection, however, needs the exact score of very few documents.  So the search path scores
 // every posting ONCE in f32 from a packed copy of the index
-//     post_pk[p] = (f32 bits of u, rounded to 11 explicit mantissa bits) | (doc index inside its 4096-doc tile)
+//     post_pk[p] = (f32 bits of u, rounded to 11 explicit mantissa bits: the upper 20 bits) |
+//                  (byte offset of the document's accumulator inside its warp's 1024-document region: bits 2..11) |
+//                  (the owning warp: bits 0..1)
 // (4 B per posting, one LDG.32 and two LOPs to decode; u = the BM25 saturation factor of post_val), with a proven bound
-// on |approx - exact| per query:
-//     eps_q = B_q * (2^-12 + (n_q + 8) * 2^-22) + tiny,  B_q = u_max * sum_t |idf_t * qtf_t|
+// on |approx - exact| per document (approx_bound_warp below): relative to the score, delta = 2^-12 + (n_q + 16) 2^-23,
+// plus 2 delta N for the negative contributions a document may have received (N = u_max * sum of |negative weights|)
 // (value rounding 2^-12 relative, f32 weight rounding and n_q fused multiply-adds 2^-24 each, f32 rounding of the exact
 // score 2^-24; any summation order).  Pipeline per batch, same launches as the exact fused path:
 //   1. MAXIMA epilogue on the sample tiles -> T = k-th largest group maximum of the APPROXIMATE scores (kth_of_maxima);
-//      k documents have approx >= T, hence exact >= T - eps, hence the exact k-th best E_k >= T - eps.
-//   2. FUSED epilogue on all tiles: candidates = touched documents with approx >= T - 2 eps (every member of the exact
-//      top-k has exact >= E_k, hence approx >= T - 2 eps).  If T <= eps (or no threshold: few matches) the query runs in
-//      "positive mode": candidates = touched documents with approx > -eps, a superset of the documents with a positive
-//      exact score; the result is accepted only if the exact k-th best is > 0, otherwise the query takes the
-//      exhaustive exact fallback (score.cu) like an overflowed list.
+//      k documents have approx >= T, hence exact >= g(T) (the lower end of the error interval), hence the exact k-th
+//      best E_k >= g(T).
+//   2. FUSED epilogue on all tiles: candidates = touched documents whose interval reaches g(T), i.e. approx >=
+//      h^-1(g(T)) (every member of the exact top-k has exact >= E_k).  If that threshold is not positive (or there is
+//      no threshold: few matches) the query runs in "positive mode": candidates = touched documents whose interval
+//      reaches above 0, a superset of the documents with a positive exact score; the result is accepted only if the
+//      exact k-th best is > 0, otherwise the query takes the exhaustive exact fallback (score.cu) like an overflowed
+//      list.
 //   3. select + rescore (one CTA per query): A_k = k-th largest approximate score among the candidates; the survivors
-//      approx >= A_k - 2 eps (k + a few documents) are rescored EXACTLY by one warp each -- the reference's f64 chain
+//      approx >= h^-1(g(A_k)) (k + a few documents) are rescored EXACTLY by one warp each -- the reference's f64 chain
 //      over the query's terms in ascending term id, postings looked up in the f64 index -- keyed, sorted, and the k best
 //      are written out.
 // "Touched": accumulators are cleared to -0.0f, and a sum that starts at -0.0 stays -0.0 only if every contribution was
@@ -30,15 +34,44 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace b2r {
 
 constexpr int AP_TILE = 4096;                // the packed format holds 12 doc bits: tile_docs must be 4096
-constexpr int AP_WARPS = 4;                  // one warp = 1024 documents = two sub-tiles of the index
+#ifndef AP_WARPS_N
+#define AP_WARPS_N 4
+#endif
+#ifndef AP_MIN_CTAS
+#define AP_MIN_CTAS 12
+#endif
+#ifndef AP_UNROLL
+#define AP_UNROLL 4
+#endif
+constexpr int AP_WARPS = AP_WARPS_N;         // one warp = 1024 documents = two sub-tiles of the index
 constexpr int AP_THREADS = 32 * AP_WARPS;
 constexpr int AP_SUB = AP_TILE / AP_WARPS;
 constexpr int AP_GROUPS_PER_TILE = 256;      // MAXIMA: group maxima per tile (must equal score.cu's SC_GROUPS_PER_TILE)
+#ifndef AP_FORMAT
+#define AP_FORMAT 2
+#endif
+// packed posting formats (derived data, rebuilt by b2r_index_pack):
+//   2: value in the upper 20 bits | byte offset of the accumulator inside its warp's 1024-document region (bits 2..11)
+//      | owning warp (bits 0..1): one LOP gives the address, the value keeps 11 explicit mantissa bits
+//   0: value in the upper 20 bits | document offset inside the tile (12 bits): LOP + shift for the address
+//   1: value in the upper 18 bits | byte offset inside the tile (bits 2..13): one LOP, but 9 mantissa bits -- the 4x
+//      wider error bound overflows the candidate lists of low-scoring queries (3 of config 2's 1024), measured slower
+#if AP_FORMAT == 1
+constexpr uint32_t AP_VAL_MASK = 0xFFFFC000u, AP_VAL_HALF = 0x2000u;
+constexpr double AP_VAL_EPS = 0x1p-10, AP_UMAX_SLACK = 1.001953125;   // value rounding; |u| <= |packed| / (1 - 2^-10)
+#else
+constexpr uint32_t AP_VAL_MASK = 0xFFFFF000u, AP_VAL_HALF = 0x800u;
+constexpr double AP_VAL_EPS = 0x1p-12, AP_UMAX_SLACK = 1.0009765625;
+#endif
+#ifndef AP_BALLOT
+#define AP_BALLOT 1     // 1: the term loop visits only the terms with postings in the tile (one vote, no shuffles for the rest)
+#endif
 constexpr uint32_t AP_NEGZERO = 0x80000000u;
 constexpr uint64_t AP_FLOOR_KEY = (0x80000000ull << 32) | 0xFFFFFFFFull;  // kth_of_maxima's "strictly positive only"
 constexpr int AP_SURV_MAX = 1024;            // survivors rescored per query; more (mass ties) -> exhaustive fallback
@@ -51,6 +84,7 @@ __device__ __align__(128) uint32_t g_negzero_page[AP_SUB];
 struct PackMeta {          // trailer of the post_pk buffer (device)
     uint32_t max_bits;     // f32 bits of max |packed value|
     uint32_t bad;          // a value was not finite: the approximate path must not be used
+    uint32_t neg;          // a value is negative: the bound cannot separate positive from negative contributions
 };
 
 __host__ __device__ static inline size_t pack_meta_offset(int64_t nnz) { return ((size_t)nnz * 4 + 255) / 256 * 256; }
@@ -58,33 +92,50 @@ __host__ __device__ static inline size_t pack_meta_offset(int64_t nnz) { return 
 __global__ void __launch_bounds__(256)
 pack_postings_kernel(const uint32_t *__restrict__ post_doc, const double *__restrict__ post_val, int64_t nnz,
                      uint32_t *__restrict__ pk, PackMeta *__restrict__ meta) {
-    uint32_t mx = 0, bad = 0;
+    uint32_t mx = 0, bad = 0, neg = 0;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
         const float v = __double2float_rn(post_val[p]);
         uint32_t r = 0;
         if (!(fabsf(v) <= 3.0e38f)) {   // inf, NaN, or so large that rounding could reach inf
             bad = 1;
         } else {
-            r = (__float_as_uint(v) + 0x800u) & 0xFFFFF000u;   // round to nearest at bit 12 (magnitude)
+            r = (__float_as_uint(v) + AP_VAL_HALF) & AP_VAL_MASK;   // round to nearest (magnitude)
         }
-        pk[p] = r | (post_doc[p] & (uint32_t)(AP_TILE - 1));
+        const uint32_t d = post_doc[p] & (uint32_t)(AP_TILE - 1);
+#if AP_FORMAT == 2
+        pk[p] = r | ((d & (uint32_t)(AP_SUB - 1)) << 2) | (d / (uint32_t)AP_SUB);
+#elif AP_FORMAT == 1
+        pk[p] = r | (d << 2);
+#else
+        pk[p] = r | d;
+#endif
         mx = max(mx, r & 0x7fffffffu);
+        neg |= (r & 0x7fffffffu) != 0 && (r >> 31);
     }
     for (int o = 16; o > 0; o >>= 1) {
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (mx) atomicMax(&meta->max_bits, mx);
         if (bad) atomicOr(&meta->bad, 1u);
+        if (neg) atomicOr(&meta->neg, 1u);
     }
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < AP_SUB; i += blockDim.x) g_negzero_page[i] = AP_NEGZERO;
 }
 
 // ---- per-query error bound and filter threshold (identical in the scoring and the selection kernel) --------------
+// For a document with exact contributions c_t (sum S, positive part P, negative part N_d) the approximate sum s obeys
+//     |s - S| <= delta * sum_t |c_t| = delta * (P + N_d) <= delta * (|S| + 2 N),   N = u_max * sum_{w_t < 0} |w_t|
+// (delta: value rounding + f32 weight rounding + n fused multiply-adds; N bounds the negative part of ANY document: the
+// packed values are >= 0 -- otherwise N is taken over all terms).  With dp = delta / (1 - delta) and c2 = 2 dp N:
+//     g(s) = s - dp |s| - c2  <=  S  <=  h(s) = s + dp |s| + c2,       g and h increasing.
+// The bound is RELATIVE to the score: a query of eight rare terms (sum |w| u_max ~ 200) with its k-th best score at 9
+// loses 0.02 of threshold, not 0.4, so the candidate lists stay as short as those of the f64 path.
 struct ApproxBound {
-    double eps;
+    double dp, c2;
     float thr_lo;   // candidates: touched && approx >= thr_lo
     int pos_mode;   // 1: accept only if the exact k-th best is > 0
     int ok;         // 0: the bound is not finite (absurd weights): the query takes the exact fallback
@@ -95,21 +146,34 @@ __device__ __forceinline__ ApproxBound approx_bound_warp(int qs, int qe, const i
                                                          const float *__restrict__ q_weights,
                                                          const float *__restrict__ idf, const PackMeta *meta,
                                                          uint64_t thr_key, int lane) {
-    double s = 0.0;
-    for (int j = qs + lane; j < qe; j += 32)
-        s = __dadd_rn(s, fabs(__dmul_rn((double)__ldg(idf + __ldg(q_terms + j)), (double)__ldg(q_weights + j))));
-    for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-    const double u_max = (double)__uint_as_float(meta->max_bits) * 1.0009765625;   // |u| <= |packed| / (1 - 2^-12)
-    const double B = __dmul_rn(s, u_max) * 1.0000001;
+    double s = 0.0, sn = 0.0;
+    for (int j = qs + lane; j < qe; j += 32) {
+        const double wq = __dmul_rn((double)__ldg(idf + __ldg(q_terms + j)), (double)__ldg(q_weights + j));
+        s = __dadd_rn(s, fabs(wq));
+        if (!(wq >= 0.0)) sn = __dadd_rn(sn, fabs(wq));   // (a NaN weight lands here too and makes the bound NaN)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        sn = __dadd_rn(sn, __shfl_xor_sync(0xffffffffu, sn, o));
+    }
+    if (meta->neg) sn = s;
+    const double u_max = (double)__uint_as_float(meta->max_bits) * AP_UMAX_SLACK;
+    const double B = __dmul_rn(s, u_max), N = __dmul_rn(sn, u_max) * 1.0000001;
     const double n = (double)(qe - qs);
+    const double delta = AP_VAL_EPS + (n + 16.0) * 0x1p-23;
     ApproxBound r;
-    r.eps = B * (0x1p-12 + (n + 8.0) * 0x1p-22) + (n + 1.0) * 0x1p-140;
-    r.ok = (r.eps == r.eps) && B < 1.0e30 && meta->bad == 0;
+    r.dp = delta / (1.0 - delta) * 1.000001;
+    r.c2 = 2.0 * r.dp * N + (n + 1.0) * 0x1p-140;
+    r.ok = (r.c2 == r.c2) && B < 1.0e30 && delta < 0.25 && meta->bad == 0;
     const uint32_t hi = (uint32_t)(thr_key >> 32);
     const bool floor_mode = thr_key == AP_FLOOR_KEY || hi <= 0x80000000u;   // no threshold, or not a positive one
     const double ta = floor_mode ? 0.0 : (double)unord_f32(hi);
-    r.pos_mode = floor_mode || !(ta > r.eps);
-    const double lo = r.pos_mode ? -r.eps : ta - 2.0 * r.eps;
+    // k sample documents have approx >= ta, hence exact >= g(ta): every member of the top-k has exact >= L (the
+    // factor covers the f32 rounding of the ranked score) and therefore h(approx) >= L
+    const double L = (ta - r.dp * ta - r.c2) * (1.0 - 0x1p-22);
+    r.pos_mode = floor_mode || !(L > r.c2);
+    const double lo = r.pos_mode ? -(r.c2 / (1.0 - r.dp)) * 1.000001 - 0x1p-130
+                                 : (L - r.c2) / (1.0 + r.dp) * (1.0 - 0x1p-20);
     r.thr_lo = __double2float_rd(lo);
     if (!r.ok) r.thr_lo = __int_as_float(0x7f800000);   // +inf: nothing qualifies; the selection kernel marks the query
     return r;
@@ -133,19 +197,44 @@ __device__ __forceinline__ void ap_mbar_wait(uint32_t bar, uint32_t parity) {
 
 // acc[doc in tile] = fma(w, value, acc) -- one LDS.32 / FFMA / STS.32 per posting.  FIRST: the warp's accumulators
 // were just cleared to -0.0, so the read is skipped (fma(w, v, -0.0) is evaluated all the same).
+// byte offset of a posting's accumulator from `base`, and the warp that owns it
+#if AP_FORMAT == 2     // base = the owning warp's region
+__device__ __forceinline__ uint32_t ap_offset(uint32_t pk) { return pk & 0xFFCu; }
+__device__ __forceinline__ uint32_t ap_owner(uint32_t pk) { return pk & 3u; }
+#elif AP_FORMAT == 1   // base = the tile
+__device__ __forceinline__ uint32_t ap_offset(uint32_t pk) { return pk & 0x3FFCu; }
+__device__ __forceinline__ uint32_t ap_owner(uint32_t pk) { return (pk & 0x3FFCu) / (4u * AP_SUB); }
+#else
+__device__ __forceinline__ uint32_t ap_offset(uint32_t pk) { return (pk & 0xFFFu) << 2; }
+__device__ __forceinline__ uint32_t ap_owner(uint32_t pk) { return (pk & 0xFFFu) / (uint32_t)AP_SUB; }
+#endif
+
+// acc[doc] = fma(w, value, acc[doc]) -- one LDS.32 / FFMA / STS.32 per posting.  FIRST: the warp's accumulators
+// were just cleared to -0.0, so the read is skipped (fma(w, v, -0.0) is evaluated all the same).
 template <bool FIRST>
-__device__ __forceinline__ void ap_apply(float *acc, uint32_t pk, float w) {
-    const uint32_t d = pk & (uint32_t)(AP_TILE - 1);
-    const float v = __uint_as_float(pk & 0xFFFFF000u);
-    const float a = FIRST ? __uint_as_float(AP_NEGZERO) : acc[d];
-    acc[d] = __fmaf_rn(w, v, a);
+__device__ __forceinline__ void ap_apply(uint32_t base_s, uint32_t pk, float w) {   // base_s: shared-window address
+    const uint32_t slot = base_s + ap_offset(pk);
+    const float v = __uint_as_float(pk & AP_VAL_MASK);
+    float a = __uint_as_float(AP_NEGZERO);
+    if (!FIRST) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(slot) : "memory");
+    const float r = __fmaf_rn(w, v, a);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(r) : "memory");
 }
 
 template <bool FIRST>
 __device__ __forceinline__ void ap_apply_term(int dense, uint32_t beg, uint32_t end, int lane, int w,
-                                              const uint32_t *__restrict__ post_pk, float *acc, float wt) {
+                                              const uint32_t *__restrict__ post_pk, uint32_t acc, float wt) {
     if (dense) {   // [beg, end) are exactly this warp's postings (its two sub-tiles are adjacent in the index)
         uint32_t p = beg + lane;
+#if AP_UNROLL == 8
+        for (; p + 224 < end; p += 256) {
+            uint32_t a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = ap_ld_stream(post_pk + p + 32 * i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ap_apply<FIRST>(acc, a[i], wt);
+        }
+#endif
         for (; p + 96 < end; p += 128) {
             const uint32_t a0 = ap_ld_stream(post_pk + p), a1 = ap_ld_stream(post_pk + p + 32);
             const uint32_t a2 = ap_ld_stream(post_pk + p + 64), a3 = ap_ld_stream(post_pk + p + 96);
@@ -158,7 +247,7 @@ __device__ __forceinline__ void ap_apply_term(int dense, uint32_t beg, uint32_t 
     } else {       // the tile's small block: every warp scans it and keeps the postings of its own 1024 documents
         for (uint32_t p = beg + lane; p < end; p += 32) {
             const uint32_t a = __ldg(post_pk + p);
-            if (((a >> 10) & 3u) == (uint32_t)w) ap_apply<FIRST>(acc, a, wt);
+            if (ap_owner(a) == (uint32_t)w) ap_apply<FIRST>(acc, a, wt);
         }
     }
 }
@@ -178,7 +267,7 @@ struct ApproxOut {
 // grid (queries, tile groups), query index fastest (co-resident CTAs share a tile's postings through L2), one CTA =
 // one query x several doc tiles (stride gridDim.y), one warp = 1024 documents whose accumulators only it touches.
 template <int OUT>
-__global__ void __launch_bounds__(AP_THREADS, 12)
+__global__ void __launch_bounds__(AP_THREADS, AP_MIN_CTAS)
 score_approx_kernel(const uint32_t *__restrict__ post_pk, const uint32_t *__restrict__ blk_ptr,
                     const int32_t *__restrict__ dense_id, const uint32_t *__restrict__ dense_ptr, int n_tiles,
                     const int32_t *__restrict__ q_ptr, const int32_t *__restrict__ q_terms,
@@ -190,6 +279,12 @@ score_approx_kernel(const uint32_t *__restrict__ post_pk, const uint32_t *__rest
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ql = blockIdx.x, q = q0 + ql;
     float *acc_w = acc + w * AP_SUB;
+#if AP_FORMAT == 2
+    static_assert(AP_WARPS == 4, "packed format 2 stores the owning warp in two bits");
+    const uint32_t acc_s = ap_smem_u32(acc_w);   // offsets are relative to the owning warp's region
+#else
+    const uint32_t acc_s = ap_smem_u32(acc);
+#endif
     const size_t dense_row = (size_t)n_tiles * B2R_SUBTILES + 1;
     constexpr int SUBS_PER_WARP = B2R_SUBTILES / AP_WARPS;
     const uint32_t zbar_a = ap_smem_u32(&zbar[w]);
@@ -274,13 +369,21 @@ score_approx_kernel(const uint32_t *__restrict__ post_pk, const uint32_t *__rest
                 ap_mbar_wait(zbar_a, zphase);
                 cleared = true;
             }
+#if AP_BALLOT
+            // (summation order is free here, but ascending term id keeps the densest term first: its postings then
+            //  take the store-only FIRST path)
+            for (unsigned live = __ballot_sync(full, lane < nt && my_beg != my_end); live; live &= live - 1) {
+                const int j = __ffs(live) - 1;
+                const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
+#else
             for (int j = 0; j < nt; ++j) {
                 const uint32_t beg = __shfl_sync(full, my_beg, j), end = __shfl_sync(full, my_end, j);
                 if (beg == end) continue;   // warp-uniform
+#endif
                 const int dense = __shfl_sync(full, my_dense, j);
                 const float wt = __shfl_sync(full, my_wt, j);
-                if (first) ap_apply_term<true>(dense, beg, end, lane, w, post_pk, acc, wt);
-                else ap_apply_term<false>(dense, beg, end, lane, w, post_pk, acc, wt);
+                if (first) ap_apply_term<true>(dense, beg, end, lane, w, post_pk, acc_s, wt);
+                else ap_apply_term<false>(dense, beg, end, lane, w, post_pk, acc_s, wt);
                 first = false;
                 __syncwarp();
             }
@@ -291,9 +394,10 @@ score_approx_kernel(const uint32_t *__restrict__ post_pk, const uint32_t *__rest
         const uint32_t doc0 = (uint32_t)tile * (uint32_t)AP_TILE + (uint32_t)w * (uint32_t)AP_SUB;
         if (OUT == AP_OUT_MAXIMA) {
             // two group maxima per lane (16 documents each); -0.0 is folded into +0.0, NaNs never win
-            float m[2];
+            constexpr int GPL = AP_SUB / 512;   // groups per lane: 16 documents each, 256 groups per tile
+            float m[GPL];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < GPL; ++g) {
                 float mm = __int_as_float(0xff800000);
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
@@ -310,9 +414,10 @@ score_approx_kernel(const uint32_t *__restrict__ post_pk, const uint32_t *__rest
                 }
                 m[g] = __fadd_rn(mm, 0.0f);
             }
-            float *out = o.maxima + (int64_t)ql * o.maxima_stride + (int64_t)y * AP_GROUPS_PER_TILE + w * 64 + lane;
-            out[0] = m[0];
-            out[32] = m[1];
+            float *out = o.maxima + (int64_t)ql * o.maxima_stride + (int64_t)y * AP_GROUPS_PER_TILE + w * (32 * GPL) +
+                         lane;
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) out[32 * g] = m[g];
         } else {
 #pragma unroll 2
             for (int it = 0; it < AP_SUB / 128; ++it) {
@@ -415,11 +520,11 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
                      const float *__restrict__ idf, const PackMeta *meta, int q0, const uint64_t *__restrict__ thr_keys,
                      const uint64_t *__restrict__ lists, int cap, int32_t *__restrict__ cnt, int k,
                      uint32_t doc_id_base, uint64_t *__restrict__ out, int64_t *__restrict__ idx_out,
-                     float *__restrict__ val_out) {
+                     float *__restrict__ val_out, int32_t *__restrict__ marked) {
     extern __shared__ uint64_t arr[];   // [cap]
     __shared__ uint64_t surv[AP_SURV_MAX];
     __shared__ uint32_t hist[256], wsum[8], s_bin, s_kk, s_n;
-    __shared__ double s_eps;
+    __shared__ double s_dp, s_c2;
     __shared__ int s_pos, s_ok;
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = q0 + row;
@@ -428,16 +533,20 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
     if (w == 0) {
         const ApproxBound ab = approx_bound_warp(qs, qe, q_terms, q_weights, idf, meta, thr_keys[row], lane);
         if (lane == 0) {
-            s_eps = ab.eps;
+            s_dp = ab.dp;
+            s_c2 = ab.c2;
             s_pos = ab.pos_mode;
             s_ok = ab.ok;
         }
     }
     __syncthreads();
     // overflowed (c > cap: already marked), short, or no usable bound: the exhaustive exact fallback takes the query
-    if (c > cap) return;
-    if (c < k || !s_ok) {
-        if (tid == 0) cnt[row] = cap + 1;
+    auto mark = [&]() {   // thread 0: hand the query to the exhaustive fallback (cnt > cap is its marker, as for an overflow)
+        cnt[row] = cap + 1;
+        marked[1 + atomicAdd(marked, 1)] = row;
+    };
+    if (c > cap || c < k || !s_ok) {
+        if (tid == 0) mark();
         return;
     }
     const uint64_t *src = lists + (int64_t)row * cap;
@@ -458,9 +567,15 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
         kk = s_kk;
         mask |= 255ull << shift;
     }
-    // survivors: approximate score >= A_k - 2 eps (compared in the ordered encoding, which is monotone)
-    const float a_k = unord_f32((uint32_t)(prefix >> 32));
-    const uint32_t lo_ord = ord_f32(__double2float_rd((double)a_k - 2.0 * s_eps));
+    // k candidates have approx >= A_k, hence exact >= G = g(A_k): a member of the top-k has exact >= G - slack (f32
+    // rounding of the ranked score) and therefore h(approx) >= G - slack, i.e. approx >= h^-1(G - slack).  Compared in
+    // the ordered encoding, which is monotone.
+    const double a_k = (double)unord_f32((uint32_t)(prefix >> 32));
+    const double G = a_k - s_dp * fabs(a_k) - s_c2;
+    const double yv = G - fabs(G) * 0x1p-22 - 0x1p-130;
+    double x0 = yv >= s_c2 ? (yv - s_c2) / (1.0 + s_dp) : (yv - s_c2) / (1.0 - s_dp);
+    x0 -= fabs(x0) * 0x1p-20;
+    const uint32_t lo_ord = ord_f32(__double2float_rd(x0));
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int i = tid; i < c; i += 256) {
@@ -473,7 +588,7 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
     __syncthreads();
     const int n = (int)s_n;
     if (n > AP_SURV_MAX || n < k) {   // (n < k cannot happen: the k best approximate keys survive)
-        if (tid == 0) cnt[row] = cap + 1;
+        if (tid == 0) mark();
         return;
     }
     // exact rescoring, one warp per survivor
@@ -494,7 +609,7 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
     // positive mode: valid only if the exact k-th best is > 0 (then no untouched / non-positive document can be in
     // the top-k); otherwise the exhaustive fallback decides
     if (s_pos && (uint32_t)(surv[k - 1] >> 32) <= 0x80000000u) {
-        if (tid == 0) cnt[row] = cap + 1;
+        if (tid == 0) mark();
         return;
     }
     for (int i = tid; i < k; i += 256) {
@@ -516,10 +631,17 @@ bool approx_usable(const b2r_index *ix, int k) {
            k >= 1 && k <= AP_SURV_MAX / 2;
 }
 
+// doc tiles walked by one CTA (B2R_AP_TILES_PER_CTA overrides it: tuning experiments only)
+static const int g_ap_tiles_per_cta = [] {
+    const char *e = getenv("B2R_AP_TILES_PER_CTA");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 64 ? v : 4;
+}();
+
 static int approx_grid_y(int nq, int n_y) {
-    // tiles per CTA: 4, fewer while the grid would not fill the GPU a few times over (148 SMs x 12 CTAs)
-    int per_cta = 4;
-    while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * 12 * 4) per_cta >>= 1;
+    // fewer tiles per CTA while the grid would not fill the GPU a few times over (148 SMs x 12 CTAs)
+    int per_cta = g_ap_tiles_per_cta;
+    while (per_cta > 1 && (int64_t)nq * (n_y / per_cta) < 148 * AP_MIN_CTAS * 4) per_cta >>= 1;
     return (n_y + per_cta - 1) / per_cta;
 }
 
@@ -561,7 +683,8 @@ int approx_fused(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_ter
 
 int approx_select(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_terms, const float *q_weights,
                   const float *idf, int q0, int nq, const uint64_t *thr, const uint64_t *cand, int32_t *cand_cnt,
-                  int cap, int k, uint64_t *keys_out, int64_t *idx_out, float *val_out, cudaStream_t st) {
+                  int cap, int k, uint64_t *keys_out, int64_t *idx_out, float *val_out, int32_t *marked,
+                  cudaStream_t st) {
     if (nq == 0) return B2R_OK;
     const size_t smem = (size_t)cap * 8;
     if (smem > 32 * 1024)
@@ -569,7 +692,7 @@ int approx_select(const b2r_index *ix, const int32_t *q_ptr, const int32_t *q_te
     approx_select_kernel<<<(unsigned)nq, 256, smem, st>>>(
         ix->post_doc, static_cast<const double *>(ix->post_val), ix->blk_ptr, ix->dense_id, ix->dense_ptr, ix->n_tiles,
         q_ptr, q_terms, q_weights, idf, meta_of(ix), q0, thr, cand, cap, cand_cnt, k, (uint32_t)ix->doc_id_base,
-        keys_out, idx_out, val_out);
+        keys_out, idx_out, val_out, marked);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }

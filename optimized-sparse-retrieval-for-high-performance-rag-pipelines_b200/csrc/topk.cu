@@ -351,7 +351,8 @@ constexpr int TL_MAX = 16384;  // longest list (dynamic shared memory: 8 bytes p
 
 __global__ void __launch_bounds__(TL_THREADS)
 topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__restrict__ cnt, int k, int min_cnt,
-                     uint64_t *__restrict__ out, int64_t *__restrict__ idx_out, float *__restrict__ val_out) {
+                     uint64_t *__restrict__ out, int64_t *__restrict__ idx_out, float *__restrict__ val_out,
+                     int32_t *__restrict__ marked) {
     extern __shared__ uint64_t arr[];   // [max(cap, 32)]
     __shared__ uint64_t best[B2R_TOPK_MAX_FAST];
     __shared__ uint32_t hist[256], wsum[8], s_bin, s_kk, s_n;
@@ -361,6 +362,7 @@ topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__res
     // a list shorter than min_cnt cannot supply the k best (its threshold was raised above the sample's k-th
     // best): mark the row for the exhaustive fallback exactly like an overflowed one (cnt > cap)
     if (tid == 0 && c < min_cnt) cnt[row] = cap + 1;
+    if (tid == 0 && marked != nullptr && (c < min_cnt || c > cap)) marked[1 + atomicAdd(marked, 1)] = row;
     c = c < 0 ? 0 : (c > cap ? cap : c);
     const uint64_t *src = lists + (int64_t)row * cap;
     for (int i = tid; i < c; i += TL_THREADS) arr[i] = src[i];
@@ -411,7 +413,7 @@ topk_of_lists_kernel(const uint64_t *__restrict__ lists, int cap, int32_t *__res
 }
 
 int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, int32_t k, int32_t min_cnt,
-                  uint64_t *keys_out, cudaStream_t st, int64_t *idx_out, float *val_out) {
+                  uint64_t *keys_out, cudaStream_t st, int64_t *idx_out, float *val_out, int32_t *marked) {
     if (n_rows == 0) return B2R_OK;
     B2R_CHECK_ARG(cap >= 1 && cap <= TL_MAX && k >= 1 && k <= cap && k <= B2R_TOPK_MAX_FAST,
                   "top-k of lists: cap=%d / k=%d unsupported", cap, k);
@@ -421,7 +423,8 @@ int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, 
     const size_t smem = (size_t)(cap > pk ? cap : pk) * 8;
     if (smem > 40 * 1024)
         B2R_CUDA(cudaFuncSetAttribute(topk_of_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, smem, st>>>(lists, cap, cnt, k, min_cnt, keys_out, idx_out, val_out);
+    topk_of_lists_kernel<<<(unsigned)n_rows, TL_THREADS, smem, st>>>(lists, cap, cnt, k, min_cnt, keys_out, idx_out, val_out,
+                                                                     marked);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }
@@ -432,7 +435,7 @@ int topk_of_lists(const uint64_t *lists, int64_t n_rows, int cap, int32_t *cnt, 
 __global__ void __launch_bounds__(256)
 kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t row_stride, int k, int lower,
                      int positive_floor, uint64_t *__restrict__ thr_out, int32_t *__restrict__ zero_a,
-                     int32_t *__restrict__ zero_b) {
+                     int32_t *__restrict__ zero_b, int32_t *__restrict__ zero_scalar) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t wsum[8];
     __shared__ uint32_t s_prefix, s_k, s_bin;
@@ -476,14 +479,16 @@ kth_of_maxima_kernel(const float *__restrict__ maxima, int64_t n_groups, int64_t
         // the row's candidate counters start at zero (saves the caller a memset node per step)
         if (zero_a) zero_a[blockIdx.x] = 0;
         if (zero_b) zero_b[blockIdx.x] = 0;
+        if (zero_scalar && blockIdx.x == 0) *zero_scalar = 0;
     }
 }
 
 int kth_of_maxima(const float *maxima, int64_t n_rows, int64_t n_groups, int64_t row_stride, int32_t k, bool lower,
-                  bool positive_floor, uint64_t *thr_out, cudaStream_t st, int32_t *zero_a, int32_t *zero_b) {
+                  bool positive_floor, uint64_t *thr_out, cudaStream_t st, int32_t *zero_a, int32_t *zero_b,
+                  int32_t *zero_scalar) {
     if (n_rows == 0) return B2R_OK;
     kth_of_maxima_kernel<<<(unsigned)n_rows, 256, 0, st>>>(maxima, n_groups, row_stride, k, lower ? 1 : 0,
-                                                           positive_floor ? 1 : 0, thr_out, zero_a, zero_b);
+                                                           positive_floor ? 1 : 0, thr_out, zero_a, zero_b, zero_scalar);
     B2R_LAUNCH_CHECK();
     return B2R_OK;
 }

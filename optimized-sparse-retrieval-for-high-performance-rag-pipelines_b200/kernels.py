@@ -44,9 +44,11 @@ def set_int8_pair(enabled: bool) -> None:
     _abi.lib.b2r_set_int8_pair(1 if enabled else 0)
 
 
-def set_bank_schedule(enabled: bool) -> None:
-    """Profiling / test hook: False makes later index builds keep dense segments doc-ascending."""
-    _abi.lib.b2r_set_bank_schedule(1 if enabled else 0)
+def set_bank_schedule(enabled) -> None:
+    """Profiling / test hook: False / 0 makes later index builds keep dense segments doc-ascending; 16 selects the
+    16-class schedule of round 1 (doc mod 16: the f64 accumulators' slots); True / anything else the default, 32
+    classes (doc mod 32: also conflict-free for the f32 accumulators of the search path's pre-filter)."""
+    _abi.lib.b2r_set_bank_schedule(int(enabled))
 
 
 def set_int8_fused(mode) -> None:
