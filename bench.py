@@ -474,6 +474,7 @@ def run_b200(args):
     lib.b2r_set_profiling(0)
     del dense
     peak, peak_src = measured_peak()
+    layout_bytes = (4 if prefiltered else 12) * postings
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     step_bytes = 12 * postings + 8 * nq * (hi - lo)
     ncu = {}
@@ -566,6 +567,12 @@ def run_b200(args):
                 "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "l2_to_sm_bytes": ncu.get("l2_to_sm_bytes"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                "kernel_layout_bytes_per_launch": layout_bytes,
+                "kernel_layout_frac": layout_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                "kernel_layout_note": ("bytes this kernel's own data layout makes it read per launch: 4 B x postings touched "
+                                       "(packed f32 pre-filter postings) -- the SURVEY figure above counts the reference "
+                                       "layout's 12 B per posting, which the pre-filter no longer moves"
+                                       if prefiltered else "12 B x postings touched (u32 doc + f64 value)"),
                 "step_model_bytes": step_bytes,
                 "step_model_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
                 "note": "step_model_* = SURVEY 8d step model 12*P + 8*N*Q; the fused path never writes or reads the "

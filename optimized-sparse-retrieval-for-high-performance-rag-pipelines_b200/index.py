@@ -319,7 +319,7 @@ class TermMajorIndex:
         several host threads run search_host concurrently (each on its own CUDA stream) against one resident index."""
         v = TermMajorIndex()
         for name in ("device", "kind", "n_docs", "n_vocab", "nnz", "tile_docs", "n_tiles", "doc_id_base", "k1", "b",
-                     "avgdl", "idf_host", "workspace_cap_bytes"):
+                     "avgdl", "idf_host", "workspace_cap_bytes", "prefilter_u_max"):
             setattr(v, name, getattr(self, name))
         v._bufs = self._bufs                    # shared, immutable after the build
         C.memmove(C.byref(v._desc), C.byref(self._desc), C.sizeof(self._desc))
