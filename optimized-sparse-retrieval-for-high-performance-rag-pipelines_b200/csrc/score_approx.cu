@@ -75,6 +75,7 @@ constexpr double AP_VAL_EPS = 0x1p-12, AP_UMAX_SLACK = 1.0009765625;
 constexpr uint32_t AP_NEGZERO = 0x80000000u;
 constexpr uint64_t AP_FLOOR_KEY = (0x80000000ull << 32) | 0xFFFFFFFFull;  // kth_of_maxima's "strictly positive only"
 constexpr int AP_SURV_MAX = 1024;            // survivors rescored per query; more (mass ties) -> exhaustive fallback
+constexpr int AP_ST_TERMS = 64;              // rescoring: queries of up to this many terms go one warp per (survivor, term)
 
 static bool g_approx_enabled = true;
 
@@ -525,11 +526,23 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
     __shared__ uint64_t surv[AP_SURV_MAX];
     __shared__ uint32_t hist[256], wsum[8], s_bin, s_kk, s_n;
     __shared__ double s_dp, s_c2;
+    __shared__ const uint32_t *st_row[AP_ST_TERMS];   // per query term: its offset row (dense: per sub-tile, else per tile)
+    __shared__ double st_idf[AP_ST_TERMS], st_qw[AP_ST_TERMS];
+    __shared__ int st_dense[AP_ST_TERMS];
     __shared__ int s_pos, s_ok;
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int q = q0 + row;
     const int qs = q_ptr[q], qe = q_ptr[q + 1];
     const int c = cnt[row];
+    if (qe - qs <= AP_ST_TERMS && tid >= 32 && tid - 32 < qe - qs) {   // stage the query's terms (warps 1..2)
+        const int j = tid - 32;
+        const int t = q_terms[qs + j];
+        const int32_t did = dense_id[t];
+        st_dense[j] = did >= 0;
+        st_row[j] = did >= 0 ? dense_ptr + (size_t)did * ((size_t)n_tiles * B2R_SUBTILES + 1) : blk_ptr + (size_t)t * n_tiles;
+        st_idf[j] = (double)idf[t];
+        st_qw[j] = (double)q_weights[qs + j];
+    }
     if (w == 0) {
         const ApproxBound ab = approx_bound_warp(qs, qe, q_terms, q_weights, idf, meta, thr_keys[row], lane);
         if (lane == 0) {
@@ -591,14 +604,60 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
         if (tid == 0) mark();
         return;
     }
-    // exact rescoring, one warp per survivor
-    for (int i = w; i < n; i += 8) {
-        const uint32_t gid = 0xFFFFFFFFu - (uint32_t)surv[i];
-        const uint32_t d = gid - doc_id_base;
-        const double s = ap_exact_score(d, qs, qe, q_terms, q_weights, idf, post_doc, post_val, blk_ptr, dense_id,
-                                        dense_ptr, n_tiles, lane);
-        __syncwarp();
-        if (lane == 0) surv[i] = make_key(ord_f32(__double2float_rn(s)), gid);
+    // exact rescoring.  Queries of <= AP_ST_TERMS terms: one warp per (survivor, term) pair looks the posting up and
+    // writes the term's contribution (idf * u) * qtf -- +0.0 when the document does not hold the term, which leaves an
+    // f64 sum that started at +0.0 unchanged bit for bit -- into the shared-memory area the candidate keys no longer
+    // need; one thread per survivor then adds them in ascending term id, the reference's summation order.  The
+    // look-ups are dependent loads: 8 warps x (n * n_terms) short chains instead of n long ones.
+    const int nt = qe - qs;
+    if (nt <= AP_ST_TERMS && nt <= cap) {
+        double *contrib = reinterpret_cast<double *>(arr);   // [batch, nt], batch * nt <= cap
+        const int batch = cap / (nt > 0 ? nt : 1);
+        for (int b0 = 0; b0 < n; b0 += batch) {
+            const int nb = min(batch, n - b0);
+            __syncthreads();   // (the keys in arr / the previous batch's contributions are no longer read)
+            for (int task = w; task < nb * nt; task += 8) {
+                const int si = task / nt, j = task - si * nt;
+                const uint32_t d = (0xFFFFFFFFu - (uint32_t)surv[b0 + si]) - doc_id_base;
+                const uint32_t tile = d / AP_TILE, sub = (d % AP_TILE) / (AP_TILE / B2R_SUBTILES);
+                const uint32_t *row = st_row[j] + (st_dense[j] ? (size_t)tile * B2R_SUBTILES + sub : (size_t)tile);
+                const uint32_t beg = __ldg(row), end = __ldg(row + 1);
+                uint32_t pos = 0xFFFFFFFFu;
+                for (uint32_t p0 = beg; p0 < end && pos == 0xFFFFFFFFu; p0 += 128) {   // warp-uniform
+                    uint32_t v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t p = p0 + 32 * i + lane;
+                        v[i] = p < end ? __ldg(post_doc + p) : 0xFFFFFFFFu;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const unsigned hit = __ballot_sync(0xffffffffu, v[i] == d);
+                        if (hit && pos == 0xFFFFFFFFu) pos = p0 + 32 * i + (__ffs(hit) - 1);
+                    }
+                }
+                if (lane == 0)
+                    contrib[task] = pos != 0xFFFFFFFFu
+                                        ? __dmul_rn(__dmul_rn(st_idf[j], __ldg(post_val + pos)), st_qw[j])
+                                        : 0.0;
+            }
+            __syncthreads();
+            for (int i = tid; i < nb; i += 256) {
+                double acc = 0.0;
+                for (int j = 0; j < nt; ++j) acc = __dadd_rn(acc, contrib[i * nt + j]);
+                const uint32_t gid = 0xFFFFFFFFu - (uint32_t)surv[b0 + i];
+                surv[b0 + i] = make_key(ord_f32(__double2float_rn(acc)), gid);
+            }
+        }
+    } else {   // long queries: one warp per survivor walks the terms
+        for (int i = w; i < n; i += 8) {
+            const uint32_t gid = 0xFFFFFFFFu - (uint32_t)surv[i];
+            const uint32_t d = gid - doc_id_base;
+            const double s = ap_exact_score(d, qs, qe, q_terms, q_weights, idf, post_doc, post_val, blk_ptr, dense_id,
+                                            dense_ptr, n_tiles, lane);
+            __syncwarp();
+            if (lane == 0) surv[i] = make_key(ord_f32(__double2float_rn(s)), gid);
+        }
     }
     int P = 32;
     while (P < n) P <<= 1;
