@@ -513,7 +513,7 @@ __device__ __forceinline__ double ap_exact_score(uint32_t d, int qs, int qe, con
     return acc;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)   // 8 x 148 CTAs resident: a 1024-query batch is one wave
 approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__restrict__ post_val,
                      const uint32_t *__restrict__ blk_ptr, const int32_t *__restrict__ dense_id,
                      const uint32_t *__restrict__ dense_ptr, int n_tiles, const int32_t *__restrict__ q_ptr,
@@ -564,26 +564,26 @@ approx_select_kernel(const uint32_t *__restrict__ post_doc, const double *__rest
     }
     const uint64_t *src = lists + (int64_t)row * cap;
     for (int i = tid; i < c; i += 256) arr[i] = src[i];
-    // k-th largest approximate key (radix select, 8 x 8 bits)
-    uint64_t prefix = 0, mask = 0;
-    uint32_t kk = (uint32_t)k;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    // k-th largest approximate SCORE, counted with multiplicity (radix select, 4 x 8 bits on the ordered encoding):
+    // the survivors are defined by a score threshold, so the document bits of the keys play no part
+    uint32_t prefix = 0, mask = 0, kk = (uint32_t)k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
         hist[tid] = 0;
         __syncthreads();
         for (int i = tid; i < c; i += 256) {
-            const uint64_t key = arr[i];
-            if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+            const uint32_t o = (uint32_t)(arr[i] >> 32);
+            if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
         }
         __syncthreads();
         ap_select_bin(hist, kk, wsum, &s_bin, &s_kk);
-        prefix |= (uint64_t)s_bin << shift;
+        prefix |= s_bin << shift;
         kk = s_kk;
-        mask |= 255ull << shift;
+        mask |= 255u << shift;
     }
     // k candidates have approx >= A_k, hence exact >= G = g(A_k): a member of the top-k has exact >= G - slack (f32
     // rounding of the ranked score) and therefore h(approx) >= G - slack, i.e. approx >= h^-1(G - slack).  Compared in
     // the ordered encoding, which is monotone.
-    const double a_k = (double)unord_f32((uint32_t)(prefix >> 32));
+    const double a_k = (double)unord_f32(prefix);
     const double G = a_k - s_dp * fabs(a_k) - s_c2;
     const double yv = G - fabs(G) * 0x1p-22 - 0x1p-130;
     double x0 = yv >= s_c2 ? (yv - s_c2) / (1.0 + s_dp) : (yv - s_c2) / (1.0 - s_dp);
