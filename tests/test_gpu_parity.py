@@ -1085,3 +1085,16 @@ def test_approx_prefilter_mass_ties_and_non_finite_values(b2r):
     finally:
         b2r.set_fused_selection(True)
     assert torch.equal(i2, p2) and np.array_equal(_bits(v2.cpu().numpy()), _bits(pv2.cpu().numpy()))
+
+
+def test_approx_prefilter_long_candidate_lists():
+    """Candidate lists of more than 4096 keys (k = 100 with a 1/64 threshold sample: the selection kernels then need
+    dynamic shared memory above the default limit): pre-filter on == f64 path.  B2R_SAMPLE_STEP is read when the
+    library is loaded, so the check runs in its own process (tools/check_bigcap.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "check_bigcap.py")], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert p.returncode == 0 and "prefilter == f64 path: True" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    assert " 8192 " in p.stdout          # the plan really used a long list
