@@ -327,3 +327,85 @@ def test_batched_document_fetch_matches_per_id_fetch(tmp_path):
         batch = svc.fetch_results({"q1": {"d10": 3.0, "d11": 2.0}, "q2": {}, "q3": {"d11": 9.0, "zzz": 1.0}})
         assert [r["id"] for r in batch["q1"]] == ["d10", "d11"] and batch["q2"] == [] and len(batch["q3"]) == 1
         assert batch["q3"][0]["metadata"] == docs[11].metadata
+
+
+def test_prefilter_error_bound_holds_on_an_emulated_corpus():
+    """The f32 pre-filter of the search path (csrc/score_approx.cu) is only allowed to rule documents out under a proven
+    bound on |approximate - exact|.  Emulate it in numpy on a seeded Zipfian corpus -- values rounded to the packed
+    format's 20 bits, f32 weights, f32 accumulation (in a DIFFERENT term order than the exact chain) -- and check the
+    three facts the kernels rely on, for Zipfian and rare-term queries, with the constants of approx_bound_warp:
+      1. g(approx) <= exact <= h(approx) for every document (g, h: the interval of the relative bound);
+      2. the candidate filter derived from the sample threshold keeps every member of the exact top-k;
+      3. the survivor filter derived from the k-th best approximate score keeps every member too.
+    (No GPU, no library call: this pins the arithmetic of the bound, the GPU tests pin the kernels.)"""
+    from oracle import np_oracle
+    sys.path.insert(0, os.path.join(ROOT, "optimized-sparse-retrieval-for-high-performance-rag-pipelines_b200"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "b2r_synthetic", os.path.join(ROOT, "optimized-sparse-retrieval-for-high-performance-rag-pipelines_b200",
+                                      "synthetic.py"))
+    S = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(S)
+    n_docs, n_vocab, k, k1, b = 120_000, 6000, 10, 1.2, 0.75
+    data, ind, ptr, dl = S.zipf_corpus(n_docs, n_vocab, 50, seed=71)
+    idf = np_oracle.idf_from_csr(ind, n_docs, n_vocab)
+    avgdl = np_oracle.avgdl_from_lengths(dl)
+    assert (idf[:5] < 0).all()
+    rows = np.repeat(np.arange(n_docs), np.diff(ptr))
+    u = (data.astype(np.float64) * (k1 + 1.0)) / (data.astype(np.float64) + k1 * (1.0 - b + b * dl.astype(np.float64)[rows] / avgdl))
+    bits = u.astype(np.float32).view(np.uint32)
+    packed = ((bits + np.uint32(0x800)) & np.uint32(0xFFFFF000)).view(np.float32)     # pack_postings_kernel
+    u_max = float(np.abs(packed).max()) * 1.0009765625
+    order = np.argsort(ind, kind="stable")                                             # term-major view
+    t_ptr = np.zeros(n_vocab + 1, np.int64)
+    np.cumsum(np.bincount(ind, minlength=n_vocab), out=t_ptr[1:])
+    t_doc, t_u, t_pk = rows[order], u[order], packed[order]
+    z = S.zipf_queries(24, n_vocab, seed=73)
+    r = S.zipf_queries(8, n_vocab, seed=74, uniform=True)
+    queries = [(z[1][z[0][i]:z[0][i + 1]], z[2][z[0][i]:z[0][i + 1]]) for i in range(24)]
+    queries += [(r[1][r[0][i]:r[0][i + 1]], r[2][r[0][i]:r[0][i + 1]]) for i in range(8)]
+    queries += [(np.array([0, 1, 2, 5]), np.ones(4, np.float32))]                      # head terms only: low scores
+    sample = np.concatenate([np.arange(t0 * 4096, min(n_docs, (t0 + 1) * 4096)) for t0 in range(0, -(-n_docs // 4096), 16)])
+    n_pos_mode = 0
+    for terms, w in queries:
+        exact = np.zeros(n_docs)
+        approx = np.zeros(n_docs, np.float32)
+        s_all = s_neg = 0.0
+        for t, qw in zip(terms, w):                                                    # exact: ascending term id
+            sl = slice(t_ptr[t], t_ptr[t + 1])
+            exact[t_doc[sl]] += (np.float64(idf[t]) * t_u[sl]) * np.float64(qw)
+        for t, qw in zip(terms[::-1], w[::-1]):                                        # approximate: any order
+            sl = slice(t_ptr[t], t_ptr[t + 1])
+            wq = np.float64(idf[t]) * np.float64(qw)
+            approx[t_doc[sl]] += np.float32(wq) * t_pk[sl]
+            s_all += abs(wq)
+            s_neg += abs(wq) if wq < 0 else 0.0
+        n = len(terms)
+        delta = 2.0 ** -12 + (n + 16) * 2.0 ** -23                                     # approx_bound_warp
+        dp = delta / (1.0 - delta) * 1.000001
+        c2 = 2.0 * dp * (s_neg * u_max * 1.0000001) + (n + 1) * 2.0 ** -140
+        a64 = approx.astype(np.float64)
+        assert (a64 - dp * np.abs(a64) - c2 <= exact).all() and (exact <= a64 + dp * np.abs(a64) + c2).all()
+        f32 = exact.astype(np.float32)
+        top = np.lexsort((np.arange(n_docs), -f32))[:k]
+        grp = approx[sample[:len(sample) // 16 * 16]].reshape(-1, 16).max(1)
+        ta = float(np.sort(grp)[-k])
+        L = (ta - dp * ta - c2) * (1.0 - 2.0 ** -22)
+        pos_mode = not (ta > 0 and L > c2)
+        lo = -(c2 / (1.0 - dp)) * 1.000001 - 2.0 ** -130 if pos_mode else (L - c2) / (1.0 + dp) * (1.0 - 2.0 ** -20)
+        touched = np.zeros(n_docs, bool)
+        for t in terms:
+            touched[t_doc[t_ptr[t]:t_ptr[t + 1]]] = True
+        cand = np.flatnonzero(touched & (approx >= np.float32(lo)))
+        n_pos_mode += pos_mode
+        if pos_mode and not (len(cand) >= k and f32[top[-1]] > 0):
+            continue                                                                   # the kernels hand these to the exact fallback
+        assert set(top.tolist()) <= set(cand.tolist())
+        a_k = float(np.sort(approx[cand])[-k])
+        G = a_k - dp * abs(a_k) - c2
+        yv = G - abs(G) * 2.0 ** -22 - 2.0 ** -130
+        x0 = (yv - c2) / (1.0 + dp) if yv >= c2 else (yv - c2) / (1.0 - dp)
+        x0 -= abs(x0) * 2.0 ** -20
+        surv = cand[approx[cand] >= np.float32(x0)]
+        assert set(top.tolist()) <= set(surv.tolist()) and len(surv) <= k + 64
+    assert n_pos_mode >= 1
