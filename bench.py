@@ -92,9 +92,10 @@ def workload_config(w):
     """The `config` object: identical in both arms (it names the workload, not the run)."""
     return {"workload": f"{w['name']}: {w['desc']}", "n_docs": w["n_docs"], "n_vocab": w["n_vocab"], "k": w["k"],
             "queries_per_step": len(w["q_ptr"]) - 1,
-            "l2": "no flush: the index (0.7 GB of postings + tables) is larger than the 126 MB L2, so every step re-reads "
-                  "the touched posting lists from HBM once; re-use ACROSS the 1024 queries of one step is served by L2 "
-                  "by design (roofline.traffic is the measured DRAM volume per launch)"}
+            "l2": "no flush: the index (0.7 GB of postings + tables, 0.2 GB of packed postings for the search path) is "
+                  "larger than the 126 MB L2, so every step re-reads the touched posting lists from HBM once; re-use "
+                  "ACROSS the 1024 queries of one step is served by L2 by design (roofline.traffic is the measured DRAM "
+                  "volume per launch)"}
 
 
 # --------------------------------------------------------------------------------------- CPU arm
