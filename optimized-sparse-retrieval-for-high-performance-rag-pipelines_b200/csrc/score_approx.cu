@@ -164,7 +164,9 @@ __device__ __forceinline__ ApproxBound approx_bound_warp(int qs, int qe, const i
     const double delta = AP_VAL_EPS + (n + 16.0) * 0x1p-23;
     ApproxBound r;
     r.dp = delta / (1.0 - delta) * 1.000001;
-    r.c2 = 2.0 * r.dp * N + (n + 1.0) * 0x1p-140;
+    // absolute slack: packed values below the normal f32 range (u < 2^-126) carry an absolute, not a relative, rounding
+    // error of at most 2^-137; results of the fused multiply-adds in the denormal range one of 2^-150 each
+    r.c2 = 2.0 * r.dp * N + s * 0x1p-135 + (n + 1.0) * 0x1p-140;
     r.ok = (r.c2 == r.c2) && B < 1.0e30 && delta < 0.25 && meta->bad == 0;
     const uint32_t hi = (uint32_t)(thr_key >> 32);
     const bool floor_mode = thr_key == AP_FLOOR_KEY || hi <= 0x80000000u;   // no threshold, or not a positive one

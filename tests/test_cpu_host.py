@@ -383,7 +383,7 @@ def test_prefilter_error_bound_holds_on_an_emulated_corpus():
         n = len(terms)
         delta = 2.0 ** -12 + (n + 16) * 2.0 ** -23                                     # approx_bound_warp
         dp = delta / (1.0 - delta) * 1.000001
-        c2 = 2.0 * dp * (s_neg * u_max * 1.0000001) + (n + 1) * 2.0 ** -140
+        c2 = 2.0 * dp * (s_neg * u_max * 1.0000001) + s_all * 2.0 ** -135 + (n + 1) * 2.0 ** -140
         a64 = approx.astype(np.float64)
         assert (a64 - dp * np.abs(a64) - c2 <= exact).all() and (exact <= a64 + dp * np.abs(a64) + c2).all()
         f32 = exact.astype(np.float32)
